@@ -1,0 +1,158 @@
+"""ctypes binding of oracle/cv_restate.c (TEST INFRASTRUCTURE ONLY)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "liboracle.so")
+
+
+def build(force=False):
+    src = os.path.join(_HERE, "cv_restate.c")
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "-s", "-B", "liboracle.so"])
+    return _SO
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(_SO)
+        _lib.or_fast_atan2.restype = C.c_float
+        _lib.or_fast_atan2.argtypes = [C.c_float, C.c_float]
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _u8(a):
+    a = np.ascontiguousarray(a)
+    assert a.dtype == np.uint8
+    return a
+
+
+def bgr2gray(bgr):
+    bgr = _u8(bgr)
+    h, w, _ = bgr.shape
+    out = np.empty((h, w), np.uint8)
+    lib().or_bgr2gray(_p(bgr), _p(out), C.c_int(h), C.c_int(w))
+    return out
+
+
+def gauss5(gray):
+    gray = _u8(gray)
+    h, w = gray.shape
+    out = np.empty_like(gray)
+    lib().or_gauss5(_p(gray), _p(out), C.c_int(h), C.c_int(w))
+    return out
+
+
+def normalize_minmax(src):
+    src = _u8(src)
+    out = np.empty_like(src)
+    lib().or_normalize_minmax(_p(src), _p(out), C.c_long(src.size))
+    return out
+
+
+def canny(src, lo, hi, return_nms=False):
+    src = _u8(src)
+    h, w = src.shape
+    out = np.empty_like(src)
+    nms = np.empty_like(src) if return_nms else None
+    lib().or_canny(_p(src), _p(out), C.c_int(h), C.c_int(w), C.c_double(lo), C.c_double(hi),
+                   _p(nms) if return_nms else None)
+    return (out, nms) if return_nms else out
+
+
+def hough_dims(h, w, rho=1.0, theta=np.pi / 180):
+    return lib().or_hough_numangle(C.c_double(theta)), lib().or_hough_numrho(C.c_int(h), C.c_int(w), C.c_double(rho))
+
+
+def hough_trig_std(rho, theta, numangle):
+    ts = np.empty(numangle, np.float32)
+    tc = np.empty(numangle, np.float32)
+    lib().or_hough_trig_std(C.c_float(rho), C.c_float(theta), C.c_int(numangle), _p(ts), _p(tc))
+    return ts, tc
+
+
+def hough_lines(edges, rho, theta, threshold, max_lines=1 << 20, return_accum=False):
+    """-> (lines (N,1,2) f32 or None, votes (N,) i32[, accum (numangle+2, numrho+2) i32])"""
+    edges = _u8(edges)
+    h, w = edges.shape
+    na, nr = hough_dims(h, w, rho, theta)
+    lines = np.empty((max_lines, 2), np.float32)
+    votes = np.empty(max_lines, np.int32)
+    accum = np.zeros((na + 2, nr + 2), np.int32)
+    n = lib().or_hough_lines(_p(edges), C.c_int(h), C.c_int(w), C.c_float(rho), C.c_float(theta),
+                             C.c_int(int(threshold)), _p(lines), _p(votes), C.c_int(max_lines), _p(accum))
+    assert n <= max_lines
+    ln = lines[:n].reshape(n, 1, 2).copy() if n else None
+    res = (ln, votes[:n].copy())
+    return res + (accum,) if return_accum else res
+
+
+def hough_lines_p(edges, rho, theta, threshold, min_len, max_gap, max_segs=1 << 18):
+    edges = _u8(edges)
+    h, w = edges.shape
+    segs = np.empty((max_segs, 4), np.int32)
+    n = lib().or_hough_lines_p(_p(edges), C.c_int(h), C.c_int(w), C.c_float(rho), C.c_float(theta),
+                               C.c_int(int(threshold)), C.c_int(int(min_len)), C.c_int(int(max_gap)),
+                               _p(segs), C.c_int(max_segs))
+    assert n <= max_segs
+    return segs[:n].reshape(n, 1, 4).copy() if n else None
+
+
+def fast_atan2(y, x):
+    return lib().or_fast_atan2(C.c_float(y), C.c_float(x))
+
+
+def gauss_taps_q8(sigma, k):
+    taps = np.empty(k, np.int32)
+    lib().or_gauss_taps_q8(C.c_double(sigma), C.c_int(k), _p(taps))
+    return taps
+
+
+def lsd_scale_image(gray, scale=0.8, sigma_scale=0.6):
+    gray = _u8(gray)
+    h, w = gray.shape
+    dh, dw = C.c_int(), C.c_int()
+    lib().or_lsd_scaled_dims(C.c_int(h), C.c_int(w), C.c_double(scale), C.byref(dh), C.byref(dw))
+    out = np.empty((dh.value, dw.value), np.uint8)
+    lib().or_lsd_scale_image(_p(gray), C.c_int(h), C.c_int(w), C.c_double(scale), C.c_double(sigma_scale), _p(out))
+    return out
+
+
+def lsd(gray, refine=0, scale=0.8, sigma_scale=0.6, quant=2.0, ang_th=22.5, log_eps=0.0, density_th=0.7,
+        n_bins=1024, max_segs=1 << 16, return_debug=False):
+    """-> (lines (N,1,4) f32 or None, width (N,1) f64, prec (N,1) f64)"""
+    assert refine in (0, 1), "oracle restates LSD_REFINE_NONE/STD only"
+    gray = _u8(gray)
+    h, w = gray.shape
+    lines = np.empty((max_segs, 4), np.float32)
+    wd = np.empty(max_segs, np.float64)
+    pr = np.empty(max_segs, np.float64)
+    dbg_s = dbg_a = None
+    if return_debug:
+        dh, dw = C.c_int(h), C.c_int(w)
+        if scale != 1:
+            lib().or_lsd_scaled_dims(C.c_int(h), C.c_int(w), C.c_double(scale), C.byref(dh), C.byref(dw))
+        dbg_s = np.empty((dh.value, dw.value), np.uint8)
+        dbg_a = np.empty((dh.value, dw.value), np.float64)
+    n = lib().or_lsd(_p(gray), C.c_int(h), C.c_int(w), C.c_int(refine), C.c_double(scale), C.c_double(sigma_scale),
+                     C.c_double(quant), C.c_double(ang_th), C.c_double(log_eps), C.c_double(density_th),
+                     C.c_int(n_bins), _p(lines), _p(wd), _p(pr), C.c_int(max_segs),
+                     _p(dbg_s) if return_debug else None, _p(dbg_a) if return_debug else None)
+    assert n <= max_segs
+    if n == 0:
+        res = (None, None, None)
+    else:
+        res = (lines[:n].reshape(n, 1, 4).copy(), wd[:n].reshape(n, 1).copy(), pr[:n].reshape(n, 1).copy())
+    return res + (dbg_s, dbg_a) if return_debug else res
