@@ -1,0 +1,678 @@
+// le_lsd.cu -- LSD line segment detector (a7), refine 0/1, for sm_100a.  Compiled with -fmad=false:
+// cv2's scalar code is unfused, and region growing feeds rounding differences back into decisions.
+//
+// Pipeline per frame (all intermediates stay in HBM scratch owned by the context):
+//   1  Q8 Gaussian (taps from the host, REFLECT_101) + exact-bilinear down-scale  -> scaled u8
+//   2  2x2 gradient: level-line angle (degrees, f32, cv2's fastAtan2 polynomial) packed in a u32
+//      with bit 31 = USED and 0xFFFFFFFF = NOTDEF; frame max of gx^2+gy^2
+//   3  stable counting sort of the DEFINED pixels by descending gradient bin (row-major in a bin):
+//      per-chunk u16 histograms -> column scan -> warp-stable scatter (match_any ranks)
+//   4  greedy region growing in that order, one WARP per frame: lanes fetch the 8 neighbours of a
+//      region point in one memory round, the accept chain (running mean angle) is warp-uniform;
+//      then the inertia rectangle (f64, sequential sums in region order like cv2).
+// Region growing is sequential inside a frame by definition (each accepted pixel moves the
+// region angle used by the next test); the data parallelism is across frames.
+#include "le_common.cuh"
+#include <vector>
+
+#define LSD_NOTDEF 0xFFFFFFFFu
+#define LSD_USED 0x80000000u
+#define D2R 0.017453292519943295  // CV_PI / 180
+
+// ------------------------------------------------------------------ 1a: generic Q8 separable blur
+#define SB_TW 64
+#define SB_TH 16
+#define SB_RMAX 8
+__global__ void __launch_bounds__(256) k_sepblur_q8(const u8 *__restrict__ src, u8 *__restrict__ dst, int h, int w,
+                                                    const int *__restrict__ taps, int r)
+{
+    __shared__ u8 g[SB_TH + 2 * SB_RMAX][SB_TW + 2 * SB_RMAX];
+    __shared__ u16 hb[SB_TH + 2 * SB_RMAX][SB_TW];
+    __shared__ int tp[2 * SB_RMAX + 1];
+    const u8 *s = src + (size_t)blockIdx.z * h * w;
+    u8 *d = dst + (size_t)blockIdx.z * h * w;
+    const int x0 = blockIdx.x * SB_TW, y0 = blockIdx.y * SB_TH;
+    const int gw = SB_TW + 2 * r, gh = SB_TH + 2 * r;
+    if (threadIdx.x < 2 * r + 1) tp[threadIdx.x] = taps[threadIdx.x];
+    for (int i = threadIdx.x; i < gh * gw; i += 256) {
+        int ty = i / gw, tx = i % gw;
+        g[ty][tx] = s[(size_t)d_reflect101(y0 + ty - r, h) * w + d_reflect101(x0 + tx - r, w)];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < gh * SB_TW; i += 256) {
+        int ty = i / SB_TW, tx = i % SB_TW;
+        u32 acc = 0;
+        for (int t = 0; t <= 2 * r; t++) acc += (u32)tp[t] * g[ty][tx + t];
+        hb[ty][tx] = (u16)acc;  // <= 255*256
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < SB_TH * SB_TW; i += 256) {
+        int ty = i / SB_TW, tx = i % SB_TW;
+        int x = x0 + tx, y = y0 + ty;
+        if (x < w && y < h) {
+            u32 acc = 0;
+            for (int t = 0; t <= 2 * r; t++) acc += (u32)tp[t] * hb[ty + t][tx];
+            d[(size_t)y * w + x] = (u8)((acc + 32768u) >> 16);
+        }
+    }
+}
+
+// ------------------------------------------------------------------ 1b: INTER_LINEAR_EXACT resize
+// xtab/ytab: (index, q8 weight of the next sample) per destination column / row, from the host
+__global__ void __launch_bounds__(256) k_resize_exact(const u8 *__restrict__ src, int h, int w, u8 *__restrict__ dst,
+                                                      int dh, int dw, const int2 *__restrict__ xtab,
+                                                      const int2 *__restrict__ ytab)
+{
+    const int f = blockIdx.z;
+    const u8 *s = src + (size_t)f * h * w;
+    u8 *d = dst + (size_t)f * dh * dw;
+    int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x >= dw || y >= dh) return;
+    int2 xt = xtab[x], yt = ytab[y];
+    int x0 = xt.x, x1 = min(x0 + 1, w - 1), y0 = yt.x, y1 = min(y0 + 1, h - 1);
+    const u8 *r0 = s + (size_t)y0 * w, *r1 = s + (size_t)y1 * w;
+    u32 a = (u32)(256 - xt.y) * r0[x0] + (u32)xt.y * r0[x1];
+    u32 b = (u32)(256 - xt.y) * r1[x0] + (u32)xt.y * r1[x1];
+    u32 v = (u32)(256 - yt.y) * a + (u32)yt.y * b;
+    d[(size_t)y * dw + x] = (u8)((v + 32768u) >> 16);
+}
+
+// ------------------------------------------------------------------ 2: gradient / level-line angle
+static __device__ __forceinline__ float d_fast_atan2(float y, float x)
+{
+    const float scale = (float)(180.0 / 3.14159265358979323846);
+    const float p1 = 0.9997878412794807f * scale, p3 = -0.3258083974640975f * scale;
+    const float p5 = 0.1555786518463281f * scale, p7 = -0.04432655554792128f * scale;
+    const float eps = 2.220446049250313e-16f;
+    float ax = fabsf(x), ay = fabsf(y), a, c, c2;
+    if (ax >= ay) {
+        c = __fdiv_rn(ay, __fadd_rn(ax, eps));
+        c2 = __fmul_rn(c, c);
+        a = __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c);
+    } else {
+        c = __fdiv_rn(ax, __fadd_rn(ay, eps));
+        c2 = __fmul_rn(c, c);
+        a = __fsub_rn(90.f, __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c));
+    }
+    if (x < 0) a = __fsub_rn(180.f, a);
+    if (y < 0) a = __fsub_rn(360.f, a);
+    return a;
+}
+
+static __device__ __forceinline__ int grad_s(const u8 *__restrict__ img, int W, int x, int y, int *gx, int *gy)
+{
+    const u8 *r0 = img + (size_t)y * W + x, *r1 = r0 + W;
+    int DA = (int)r1[1] - (int)r0[0], BC = (int)r0[1] - (int)r1[0];
+    *gx = DA + BC;
+    *gy = DA - BC;
+    return *gx * *gx + *gy * *gy;
+}
+
+__global__ void __launch_bounds__(256) k_lsd_grad(const u8 *__restrict__ img, u32 *__restrict__ ang,
+                                                  int *__restrict__ counters, int H, int W, int s_thr)
+{
+    const int f = blockIdx.z;
+    const u8 *im = img + (size_t)f * H * W;
+    u32 *an = ang + (size_t)f * H * W;
+    int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    int smax = 0;
+    if (x < W && y < H) {
+        u32 out = LSD_NOTDEF;
+        if (x < W - 1 && y < H - 1) {
+            int gx, gy;
+            int s = grad_s(im, W, x, y, &gx, &gy);
+            if (s > s_thr) {  // sqrt(s/4.0) > rho, threshold resolved on the host in f64
+                out = __float_as_uint(d_fast_atan2((float)gx, (float)-gy));
+                smax = s;
+            }
+        }
+        an[(size_t)y * W + x] = out;
+    }
+    for (int o = 16; o; o >>= 1) smax = max(smax, __shfl_xor_sync(~0u, smax, o));
+    if ((threadIdx.x & 31) == 0 && smax > 0) atomicMax(&counters[f * LE_C_STRIDE + LE_C_MAX], smax);
+}
+
+// ------------------------------------------------------------------ 3: stable counting sort
+#define LS_CHUNK 2048
+static __device__ __forceinline__ int lsd_bin(int s, double bin_coef, int n_bins)
+{
+    int b = (int)(sqrt((double)s / 4.0) * bin_coef);
+    return min(b, n_bins - 1);
+}
+static __device__ __forceinline__ double lsd_bin_coef(const int *counters, int f, int n_bins)
+{
+    int smax = counters[f * LE_C_STRIDE + LE_C_MAX];
+    return smax > 0 ? (double)(n_bins - 1) / sqrt((double)smax / 4.0) : 0.0;
+}
+
+// per-chunk histogram (u16) of defined pixels; chunk = LS_CHUNK consecutive pixels (row-major)
+__global__ void __launch_bounds__(256) k_lsd_hist(const u8 *__restrict__ img, const u32 *__restrict__ ang,
+                                                  const int *__restrict__ counters, u16 *__restrict__ chist, int H,
+                                                  int W, int nchunk, int n_bins)
+{
+    extern __shared__ u32 sh[];  // n_bins counters
+    const int f = blockIdx.y, c = blockIdx.x;
+    const size_t npx = (size_t)H * W;
+    const u8 *im = img + (size_t)f * npx;
+    const u32 *an = ang + (size_t)f * npx;
+    for (int i = threadIdx.x; i < n_bins; i += 256) sh[i] = 0;
+    __syncthreads();
+    const double coef = lsd_bin_coef(counters, f, n_bins);
+    size_t b0 = (size_t)c * LS_CHUNK, b1 = min(npx, b0 + LS_CHUNK);
+    for (size_t i = b0 + threadIdx.x; i < b1; i += 256) {
+        if (an[i] != LSD_NOTDEF) {
+            int y = (int)(i / W), x = (int)(i - (size_t)y * W), gx, gy;
+            atomicAdd(&sh[lsd_bin(grad_s(im, W, x, y, &gx, &gy), coef, n_bins)], 1u);
+        }
+    }
+    __syncthreads();
+    u16 *o = chist + ((size_t)f * nchunk + c) * n_bins;
+    for (int i = threadIdx.x; i < n_bins; i += 256) o[i] = (u16)sh[i];
+}
+
+// offsets: for bin b (descending order) and chunk c (ascending): start position in the ordered list.
+// One block per frame, thread per bin for the chunk-direction scan, then a block scan over bins.
+__global__ void __launch_bounds__(1024) k_lsd_scan(u16 *__restrict__ chist, u32 *__restrict__ coff,
+                                                   int *__restrict__ counters, int nchunk, int n_bins)
+{
+    extern __shared__ u32 tot[];  // n_bins totals, then bin starts
+    const int f = blockIdx.x;
+    for (int b = threadIdx.x; b < n_bins; b += blockDim.x) {
+        u32 acc = 0;
+        for (int c = 0; c < nchunk; c++) {
+            size_t k = ((size_t)f * nchunk + c) * n_bins + b;
+            u32 v = chist[k];
+            coff[k] = acc;  // offset of this chunk inside the bin
+            acc += v;
+        }
+        tot[b] = acc;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        u32 acc = 0;
+        for (int b = n_bins - 1; b >= 0; b--) {
+            u32 v = tot[b];
+            tot[b] = acc;
+            acc += v;
+        }
+        counters[f * LE_C_STRIDE + LE_C_AUX0] = (int)acc;  // number of defined pixels
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b < n_bins; b += blockDim.x) {
+        u32 st = tot[b];
+        for (int c = 0; c < nchunk; c++) coff[((size_t)f * nchunk + c) * n_bins + b] += st;
+    }
+}
+
+// stable scatter: one warp per chunk walks its pixels in row-major order, 32 at a time
+__global__ void __launch_bounds__(32) k_lsd_scatter(const u8 *__restrict__ img, const u32 *__restrict__ ang,
+                                                    const int *__restrict__ counters, const u32 *__restrict__ coff,
+                                                    u32 *__restrict__ order, int H, int W, int nchunk, int n_bins)
+{
+    extern __shared__ u32 off[];  // n_bins running offsets of this chunk
+    const int f = blockIdx.y, c = blockIdx.x, lane = threadIdx.x;
+    const size_t npx = (size_t)H * W;
+    const u8 *im = img + (size_t)f * npx;
+    const u32 *an = ang + (size_t)f * npx;
+    u32 *ord = order + (size_t)f * npx;
+    const u32 *co = coff + ((size_t)f * nchunk + c) * n_bins;
+    for (int i = lane; i < n_bins; i += 32) off[i] = co[i];
+    __syncwarp();
+    const double coef = lsd_bin_coef(counters, f, n_bins);
+    size_t b0 = (size_t)c * LS_CHUNK, b1 = min(npx, b0 + LS_CHUNK);
+    for (size_t i0 = b0; i0 < b1; i0 += 32) {
+        size_t i = i0 + lane;
+        bool def = i < b1 && an[i] != LSD_NOTDEF;
+        int bin = -1 - lane;  // unique negative keys for undefined lanes
+        if (def) {
+            int y = (int)(i / W), x = (int)(i - (size_t)y * W), gx, gy;
+            bin = lsd_bin(grad_s(im, W, x, y, &gx, &gy), coef, n_bins);
+        }
+        u32 peers = __match_any_sync(~0u, bin);
+        if (def) {
+            int rank = __popc(peers & ((1u << lane) - 1));
+            u32 base = off[bin];
+            ord[base + rank] = (u32)i;
+            __syncwarp(peers);
+            if (rank == __popc(peers) - 1) off[bin] = base + rank + 1;
+        }
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------ 4: region growing + rectangle
+struct LsdParams {
+    int H, W, n_bins, refine, max_segs;
+    unsigned min_reg_size;
+    double prec, p, scale, density_th;
+};
+
+static __device__ __forceinline__ bool aligned_to(double theta, double a, double prec)
+{
+    double n_theta = theta - a;
+    if (n_theta < 0) n_theta = -n_theta;
+    if (n_theta > 4.71238898038468985769) {  // 3*pi/2
+        n_theta -= 6.28318530717958647692;
+        if (n_theta < 0) n_theta = -n_theta;
+    }
+    return n_theta <= prec;
+}
+static __device__ __forceinline__ double angle_diff_signed(double a, double b)
+{
+    double diff = a - b;
+    while (diff <= -3.14159265358979323846) diff += 6.28318530717958647692;
+    while (diff > 3.14159265358979323846) diff -= 6.28318530717958647692;
+    return diff;
+}
+
+struct LsdRect {
+    double x1, y1, x2, y2, width, x, y, theta, dx, dy;
+};
+
+// grow from seed (sx, sy); returns region size.  Warp-uniform; lane k<9 prefetches neighbour k.
+static __device__ int lsd_grow(volatile u32 *an, u32 *reg, int W, int H, int sx, int sy, double tol,
+                               double *reg_angle_out, int lane)
+{
+    int n = 0;
+    u32 sv = an[(size_t)sy * W + sx] & ~LSD_USED;
+    double reg_angle = (double)__uint_as_float(sv) * D2R;
+    if (lane == 0) {
+        reg[0] = ((u32)sy << 16) | (u32)sx;
+        an[(size_t)sy * W + sx] = sv | LSD_USED;
+    }
+    n = 1;
+    float sumdx = (float)cos(reg_angle), sumdy = (float)sin(reg_angle);
+    __syncwarp();
+    const int ky = lane / 3 - 1, kx = lane % 3 - 1;
+    for (int i = 0; i < n; i++) {
+        u32 pt = ((volatile u32 *)reg)[i];
+        int px = (int)(pt & 0xffff), py = (int)(pt >> 16);
+        int xx = px + kx, yy = py + ky;
+        u32 v = LSD_NOTDEF;
+        if (lane < 9 && xx >= 0 && xx < W && yy >= 0 && yy < H) v = an[(size_t)yy * W + xx];
+#pragma unroll
+        for (int k = 0; k < 9; k++) {
+            u32 vk = __shfl_sync(~0u, v, k);
+            if (vk == LSD_NOTDEF || (vk & LSD_USED)) continue;  // warp-uniform
+            double a = (double)__uint_as_float(vk) * D2R;
+            if (!aligned_to(reg_angle, a, tol)) continue;
+            int ax = px + (k % 3) - 1, ay = py + (k / 3) - 1;
+            if (lane == 0) {
+                an[(size_t)ay * W + ax] = vk | LSD_USED;
+                reg[n] = ((u32)ay << 16) | (u32)ax;
+            }
+            n++;
+            float af = (float)a;
+            sumdx += (float)cos((double)af);
+            sumdy += (float)sin((double)af);
+            reg_angle = (double)d_fast_atan2(sumdy, sumdx) * D2R;
+        }
+        __syncwarp();
+    }
+    *reg_angle_out = reg_angle;
+    return n;
+}
+
+// rectangle from a region (cv2 region2rect + get_theta); sums run in region order like cv2.
+static __device__ void lsd_region2rect(const u8 *__restrict__ im, const u32 *reg, int n, int W, double reg_angle,
+                                       double prec, LsdRect *rec, int lane)
+{
+    double x = 0, y = 0, sum = 0;
+    for (int i0 = 0; i0 < n; i0 += 32) {
+        int i = i0 + lane;
+        u32 pt = 0;
+        double wgt = 0;
+        if (i < n) {
+            pt = ((volatile const u32 *)reg)[i];
+            int gx, gy;
+            wgt = sqrt((double)grad_s(im, W, (int)(pt & 0xffff), (int)(pt >> 16), &gx, &gy) / 4.0);
+        }
+        int cnt = min(32, n - i0);
+        for (int j = 0; j < cnt; j++) {
+            u32 pj = __shfl_sync(~0u, pt, j);
+            double wj = __shfl_sync(~0u, wgt, j);
+            x += (double)(int)(pj & 0xffff) * wj;
+            y += (double)(int)(pj >> 16) * wj;
+            sum += wj;
+        }
+    }
+    x /= sum;
+    y /= sum;
+    double Ixx = 0, Iyy = 0, Ixy = 0;
+    for (int i0 = 0; i0 < n; i0 += 32) {
+        int i = i0 + lane;
+        u32 pt = 0;
+        double wgt = 0;
+        if (i < n) {
+            pt = ((volatile const u32 *)reg)[i];
+            int gx, gy;
+            wgt = sqrt((double)grad_s(im, W, (int)(pt & 0xffff), (int)(pt >> 16), &gx, &gy) / 4.0);
+        }
+        int cnt = min(32, n - i0);
+        for (int j = 0; j < cnt; j++) {
+            u32 pj = __shfl_sync(~0u, pt, j);
+            double wj = __shfl_sync(~0u, wgt, j);
+            double dx = (double)(int)(pj & 0xffff) - x, dy = (double)(int)(pj >> 16) - y;
+            Ixx += dy * dy * wj;
+            Iyy += dx * dx * wj;
+            Ixy -= dx * dy * wj;
+        }
+    }
+    double lambda = 0.5 * (Ixx + Iyy - sqrt((Ixx - Iyy) * (Ixx - Iyy) + 4.0 * Ixy * Ixy));
+    double theta = (fabs(Ixx) > fabs(Iyy)) ? (double)d_fast_atan2((float)(lambda - Ixx), (float)Ixy)
+                                           : (double)d_fast_atan2((float)Ixy, (float)(lambda - Iyy));
+    theta *= D2R;
+    if (fabs(angle_diff_signed(theta, reg_angle)) > prec) theta += 3.14159265358979323846;
+    double dx = cos(theta), dy = sin(theta);
+    double l_min = 0, l_max = 0, w_min = 0, w_max = 0;
+    for (int i = lane; i < n; i += 32) {
+        u32 pt = ((volatile const u32 *)reg)[i];
+        double rdx = (double)(int)(pt & 0xffff) - x, rdy = (double)(int)(pt >> 16) - y;
+        double l = rdx * dx + rdy * dy, wv = -rdx * dy + rdy * dx;
+        l_max = fmax(l_max, l);
+        l_min = fmin(l_min, l);
+        w_max = fmax(w_max, wv);
+        w_min = fmin(w_min, wv);
+    }
+    for (int o = 16; o; o >>= 1) {
+        l_max = fmax(l_max, __shfl_xor_sync(~0u, l_max, o));
+        l_min = fmin(l_min, __shfl_xor_sync(~0u, l_min, o));
+        w_max = fmax(w_max, __shfl_xor_sync(~0u, w_max, o));
+        w_min = fmin(w_min, __shfl_xor_sync(~0u, w_min, o));
+    }
+    rec->x1 = x + l_min * dx;
+    rec->y1 = y + l_min * dy;
+    rec->x2 = x + l_max * dx;
+    rec->y2 = y + l_max * dy;
+    rec->width = w_max - w_min;
+    rec->x = x;
+    rec->y = y;
+    rec->theta = theta;
+    rec->dx = dx;
+    rec->dy = dy;
+    if (rec->width < 1.0) rec->width = 1.0;
+}
+
+static __device__ __forceinline__ double dist2d(double x1, double y1, double x2, double y2)
+{
+    return sqrt((x2 - x1) * (x2 - x1) + (y2 - y1) * (y2 - y1));
+}
+
+// LSD_REFINE_STD (cv2 refine + reduce_region_radius); returns false if the region is rejected
+static __device__ bool lsd_refine(const u8 *__restrict__ im, volatile u32 *an, u32 *reg, int *pn, int W, int H,
+                                  double *reg_angle, double prec, LsdRect *rec, double density_th, int lane)
+{
+    int n = *pn;
+    double density = (double)n / (dist2d(rec->x1, rec->y1, rec->x2, rec->y2) * rec->width);
+    if (density >= density_th) return true;
+    u32 p0 = ((volatile u32 *)reg)[0];
+    const int sx = (int)(p0 & 0xffff), sy = (int)(p0 >> 16);
+    const double xc = (double)sx, yc = (double)sy;
+    const double ang_c = (double)__uint_as_float(an[(size_t)sy * W + sx] & ~LSD_USED) * D2R;
+    double sum = 0, s_sum = 0;
+    int cnt = 0;
+    for (int i0 = 0; i0 < n; i0 += 32) {
+        int i = i0 + lane;
+        double ang_d = 0;
+        bool in = false;
+        if (i < n) {
+            u32 pt = ((volatile u32 *)reg)[i];
+            int px = (int)(pt & 0xffff), py = (int)(pt >> 16);
+            u32 v = an[(size_t)py * W + px] & ~LSD_USED;
+            an[(size_t)py * W + px] = v;  // NOTUSED
+            if (dist2d(xc, yc, (double)px, (double)py) < rec->width) {
+                in = true;
+                ang_d = angle_diff_signed((double)__uint_as_float(v) * D2R, ang_c);
+            }
+        }
+        u32 bal = __ballot_sync(~0u, in);
+        while (bal) {  // sequential in region order
+            int j = __ffs(bal) - 1;
+            bal &= bal - 1;
+            double dj = __shfl_sync(~0u, ang_d, j);
+            sum += dj;
+            s_sum += dj * dj;
+            ++cnt;
+        }
+    }
+    __syncwarp();
+    double mean_angle = sum / (double)cnt;
+    double tau = 2.0 * sqrt((s_sum - 2.0 * mean_angle * sum) / (double)cnt + mean_angle * mean_angle);
+    n = lsd_grow(an, reg, W, H, sx, sy, tau, reg_angle, lane);
+    *pn = n;
+    if (n < 2) return false;
+    lsd_region2rect(im, reg, n, W, *reg_angle, prec, rec, lane);
+    density = (double)n / (dist2d(rec->x1, rec->y1, rec->x2, rec->y2) * rec->width);
+    if (density >= density_th) return true;
+    // reduce_region_radius
+    double radSq1 = (xc - rec->x1) * (xc - rec->x1) + (yc - rec->y1) * (yc - rec->y1);
+    double radSq2 = (xc - rec->x2) * (xc - rec->x2) + (yc - rec->y2) * (yc - rec->y2);
+    double radSq = radSq1 > radSq2 ? radSq1 : radSq2;
+    while (density < density_th) {
+        radSq *= 0.75 * 0.75;
+        // swap-with-last removal in cv2's exact order (sequential; regions here are small)
+        if (lane == 0) {
+            for (int i = 0; i < n; i++) {
+                u32 pt = reg[i];
+                int px = (int)(pt & 0xffff), py = (int)(pt >> 16);
+                double ddx = (double)px - xc, ddy = (double)py - yc;
+                if (ddx * ddx + ddy * ddy > radSq) {
+                    an[(size_t)py * W + px] &= ~LSD_USED;
+                    reg[i] = reg[n - 1];
+                    reg[n - 1] = pt;
+                    n--;
+                    i--;
+                }
+            }
+        }
+        n = __shfl_sync(~0u, n, 0);
+        __syncwarp();
+        *pn = n;
+        if (n < 2) return false;
+        lsd_region2rect(im, reg, n, W, *reg_angle, prec, rec, lane);
+        density = (double)n / (dist2d(rec->x1, rec->y1, rec->x2, rec->y2) * rec->width);
+    }
+    return true;
+}
+
+__global__ void __launch_bounds__(32) k_lsd_grow(const u8 *__restrict__ img, u32 *__restrict__ ang,
+                                                 const u32 *__restrict__ order, u32 *__restrict__ regbuf,
+                                                 const int *__restrict__ counters, LsdParams P,
+                                                 float *__restrict__ segs, double *__restrict__ widths,
+                                                 double *__restrict__ precs, int32_t *__restrict__ counts)
+{
+    const int f = blockIdx.x, lane = threadIdx.x;
+    const int W = P.W, H = P.H;
+    const size_t npx = (size_t)H * W;
+    const u8 *im = img + (size_t)f * npx;
+    volatile u32 *an = ang + (size_t)f * npx;
+    const u32 *ord = order + (size_t)f * npx;
+    u32 *reg = regbuf + (size_t)f * npx;
+    const int ndef = counters[f * LE_C_STRIDE + LE_C_AUX0];
+    int nseg = 0;
+    for (int i0 = 0; i0 < ndef; i0 += 32) {
+        u32 mine = (i0 + lane < ndef) ? ord[i0 + lane] : 0;
+        int cnt = min(32, ndef - i0);
+        for (int j = 0; j < cnt; j++) {
+            u32 pidx = __shfl_sync(~0u, mine, j);
+            u32 v = an[pidx];
+            if (v & LSD_USED) continue;  // (NOTDEF has bit 31 set too, but only defined pixels are listed)
+            int sy = (int)(pidx / (u32)W), sx = (int)(pidx - (u32)sy * W);
+            double reg_angle;
+            int n = lsd_grow(an, reg, W, H, sx, sy, P.prec, &reg_angle, lane);
+            if ((unsigned)n < P.min_reg_size) continue;
+            LsdRect rec;
+            lsd_region2rect(im, reg, n, W, reg_angle, P.prec, &rec, lane);
+            if (P.refine > 0) {
+                if (!lsd_refine(im, an, reg, &n, W, H, &reg_angle, P.prec, &rec, P.density_th, lane)) continue;
+            }
+            rec.x1 += 0.5; rec.y1 += 0.5; rec.x2 += 0.5; rec.y2 += 0.5;
+            if (P.scale != 1) {
+                rec.x1 /= P.scale; rec.y1 /= P.scale; rec.x2 /= P.scale; rec.y2 /= P.scale;
+                rec.width /= P.scale;
+            }
+            if (lane == 0 && nseg < P.max_segs) {
+                float *o = segs + ((size_t)f * P.max_segs + nseg) * 4;
+                o[0] = (float)rec.x1; o[1] = (float)rec.y1; o[2] = (float)rec.x2; o[3] = (float)rec.y2;
+                if (widths) widths[(size_t)f * P.max_segs + nseg] = rec.width;
+                if (precs) precs[(size_t)f * P.max_segs + nseg] = P.p;
+            }
+            nseg++;
+        }
+    }
+    if (lane == 0) counts[f] = nseg;
+}
+
+// ------------------------------------------------------------------ host side
+extern "C" int le_lsd_scaled_dims(int h, int w, double scale, int *sh, int *sw)
+{
+    if (!sh || !sw || h <= 0 || w <= 0 || !(scale > 0)) return LE_ERR_INVALID;
+    *sw = scale != 1 ? (int)lrint(w * scale) : w;
+    *sh = scale != 1 ? (int)lrint(h * scale) : h;
+    return LE_OK;
+}
+
+static void gauss_taps_q8(double sigma, int k, std::vector<int> &taps)
+{
+    std::vector<double> ker(k);
+    double sum = 0, scale2x = -0.5 / (sigma * sigma);
+    for (int i = 0; i < k; i++) {
+        double x = i - (k - 1) * 0.5;
+        ker[i] = exp(scale2x * x * x);
+        sum += ker[i];
+    }
+    for (int i = 0; i < k; i++) ker[i] /= sum;
+    taps.assign(k, 0);
+    double err = 0;
+    long tot = 0;
+    for (int i = 0; i < k / 2; i++) {
+        double adj = ker[i] * 256.0 + err;
+        long v0 = lrint(adj);
+        err = adj - (double)v0;
+        taps[i] = taps[k - 1 - i] = (int)v0;
+        tot += v0;
+    }
+    taps[k / 2] = (int)(256 - 2 * tot);
+}
+
+static void resize_tab(int src, int dst, double inv_scale, std::vector<int2> &tab)
+{
+    tab.resize(dst);
+    double sc = 1.0 / inv_scale;
+    for (int d = 0; d < dst; d++) {
+        double pos = (d + 0.5) * sc - 0.5;
+        int i = (int)floor(pos);
+        double fr = pos - i;
+        if (i < 0) { i = 0; fr = 0; }
+        if (i >= src - 1) { i = src - 1; fr = 0; }
+        tab[d] = make_int2(i, (int)lrint(fr * 256.0));
+    }
+}
+
+__global__ void k_lsd_zero(int *counters, int n)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        counters[i * LE_C_STRIDE + LE_C_MAX] = 0;
+        counters[i * LE_C_STRIDE + LE_C_AUX0] = 0;
+    }
+}
+
+extern "C" int le_lsd(le_ctx *ctx, const uint8_t *gray, int n, int h, int w, int refine, double scale,
+                      double sigma_scale, double quant, double ang_th, double log_eps, double density_th, int n_bins,
+                      float *segs, double *width, double *prec_out, int32_t *counts, int max_segs, void *stream)
+{
+    (void)log_eps;
+    if (!ctx) return LE_ERR_INVALID;
+    LE_REQUIRE(ctx, gray && segs && counts, "null pointer");
+    LE_REQUIRE(ctx, n > 0 && h > 1 && w > 1 && max_segs > 0, "n, h, w, max_segs must be positive");
+    LE_REQUIRE(ctx, h < 65536 && w < 65536, "frame too large");
+    LE_REQUIRE(ctx, scale > 0 && sigma_scale > 0 && quant >= 0 && ang_th > 0 && ang_th < 180, "bad LSD parameters");
+    LE_REQUIRE(ctx, n_bins > 0 && n_bins <= 8192, "n_bins must be in 1..8192");
+    if (refine != 0 && refine != 1)
+        return le_fail(ctx, LE_ERR_UNSUPPORTED, "LSD refine=%d (LSD_REFINE_ADV) has no GPU path yet", refine);
+    cudaSetDevice(ctx->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    int H = h, W = w;
+    le_lsd_scaled_dims(h, w, scale, &H, &W);
+    LE_REQUIRE(ctx, H > 1 && W > 1, "scaled image too small");
+    const size_t npx = (size_t)H * W;
+    const int nchunk = (int)((npx + LS_CHUNK - 1) / LS_CHUNK);
+    int rc;
+    if ((rc = le_ensure(ctx, &ctx->counters, sizeof(int) * LE_C_STRIDE * (size_t)n))) return rc;
+    if ((rc = le_ensure(ctx, &ctx->lsd1, npx * n))) return rc;                                 // scaled image
+    if ((rc = le_ensure(ctx, &ctx->lsd2, sizeof(u32) * npx * n))) return rc;                   // angles
+    if ((rc = le_ensure(ctx, &ctx->lsd3, sizeof(u32) * npx * n))) return rc;                   // order
+    if ((rc = le_ensure(ctx, &ctx->lsd4, sizeof(u32) * npx * n))) return rc;                   // region list
+    if ((rc = le_ensure(ctx, &ctx->lsd5, (sizeof(u16) + sizeof(u32)) * (size_t)nchunk * n_bins * n + 16))) return rc;
+    ctx->edge_list_for = nullptr;
+    const u8 *img = gray;
+    LE_T0(ctx, LE_K_LSD_PREP, st);
+    if (scale != 1) {
+        const double sigma = (scale < 1) ? (sigma_scale / scale) : sigma_scale;
+        const unsigned hh = (unsigned)ceil(sigma * sqrt(2 * 3.0 * log(10.0)));
+        const int k = 1 + 2 * (int)hh;
+        LE_REQUIRE(ctx, hh <= SB_RMAX, "Gaussian kernel too large (sigma_scale / scale)");
+        std::vector<int> taps;
+        gauss_taps_q8(sigma, k, taps);
+        std::vector<int2> xt, yt;
+        resize_tab(w, W, scale, xt);
+        resize_tab(h, H, scale, yt);
+        size_t tab_bytes = 128 + sizeof(int2) * ((size_t)W + H);
+        if ((rc = le_ensure(ctx, &ctx->lsd_tab, tab_bytes))) return rc;
+        if ((rc = le_ensure(ctx, &ctx->lsd0, (size_t)h * w * n))) return rc;  // blurred full-res
+        char *tb = (char *)ctx->lsd_tab.p;
+        if (!(ctx->lsd_key[0] == h && ctx->lsd_key[1] == w && ctx->lsd_key[2] == scale && ctx->lsd_key[3] == sigma_scale)) {
+            // pageable-source copies are staged before cudaMemcpyAsync returns
+            LE_CUDA(ctx, cudaMemcpyAsync(tb, taps.data(), sizeof(int) * k, cudaMemcpyHostToDevice, st));
+            LE_CUDA(ctx, cudaMemcpyAsync(tb + 128, xt.data(), sizeof(int2) * W, cudaMemcpyHostToDevice, st));
+            LE_CUDA(ctx, cudaMemcpyAsync(tb + 128 + sizeof(int2) * W, yt.data(), sizeof(int2) * H, cudaMemcpyHostToDevice, st));
+            ctx->lsd_key[0] = h; ctx->lsd_key[1] = w; ctx->lsd_key[2] = scale; ctx->lsd_key[3] = sigma_scale;
+        }
+        k_sepblur_q8<<<dim3((w + SB_TW - 1) / SB_TW, (h + SB_TH - 1) / SB_TH, n), 256, 0, st>>>(
+            gray, (u8 *)ctx->lsd0.p, h, w, (const int *)tb, (int)hh);
+        LE_LAUNCH_CHECK(ctx);
+        k_resize_exact<<<dim3((W + 31) / 32, (H + 7) / 8, n), 256, 0, st>>>(
+            (const u8 *)ctx->lsd0.p, h, w, (u8 *)ctx->lsd1.p, H, W, (const int2 *)(tb + 128),
+            (const int2 *)(tb + 128 + sizeof(int2) * W));
+        LE_LAUNCH_CHECK(ctx);
+        img = (const u8 *)ctx->lsd1.p;
+    }
+    LsdParams P;
+    P.H = H; P.W = W; P.n_bins = n_bins; P.refine = refine; P.max_segs = max_segs;
+    P.prec = M_PI * ang_th / 180;
+    P.p = ang_th / 180;
+    P.scale = scale;
+    P.density_th = density_th;
+    const double rho = quant / sin(P.prec);
+    // largest integer s with sqrt(s/4.0) <= rho (so "defined" is s > s_thr)
+    int s_thr = (int)floor(4.0 * rho * rho);
+    while (s_thr >= 0 && !(sqrt((double)s_thr / 4.0) <= rho)) s_thr--;
+    while (sqrt((double)(s_thr + 1) / 4.0) <= rho) s_thr++;
+    const double LOG_NT = 5 * (log10((double)W) + log10((double)H)) / 2 + log10(11.0);
+    P.min_reg_size = (unsigned)(size_t)(-LOG_NT / log10(P.p));
+    int *cnt = (int *)ctx->counters.p;
+    k_lsd_zero<<<(n + 255) / 256, 256, 0, st>>>(cnt, n);
+    LE_LAUNCH_CHECK(ctx);
+    k_lsd_grad<<<dim3((W + 31) / 32, (H + 7) / 8, n), 256, 0, st>>>(img, (u32 *)ctx->lsd2.p, cnt, H, W, s_thr);
+    LE_LAUNCH_CHECK(ctx);
+    u16 *chist = (u16 *)ctx->lsd5.p;
+    u32 *coff = (u32 *)((char *)ctx->lsd5.p + sizeof(u16) * (size_t)nchunk * n_bins * n);
+    // coff must be 4-byte aligned: nchunk*n_bins*n*2 is even*... force alignment
+    coff = (u32 *)(((size_t)coff + 3) & ~(size_t)3);
+    k_lsd_hist<<<dim3(nchunk, n), 256, sizeof(u32) * n_bins, st>>>(img, (const u32 *)ctx->lsd2.p, cnt, chist, H, W,
+                                                                    nchunk, n_bins);
+    LE_LAUNCH_CHECK(ctx);
+    k_lsd_scan<<<n, 1024, sizeof(u32) * n_bins, st>>>(chist, coff, cnt, nchunk, n_bins);
+    LE_LAUNCH_CHECK(ctx);
+    k_lsd_scatter<<<dim3(nchunk, n), 32, sizeof(u32) * n_bins, st>>>(img, (const u32 *)ctx->lsd2.p, cnt, coff,
+                                                                     (u32 *)ctx->lsd3.p, H, W, nchunk, n_bins);
+    LE_LAUNCH_CHECK(ctx);
+    LE_T1(ctx, LE_K_LSD_PREP, st);
+    LE_T0(ctx, LE_K_LSD_GROW, st);
+    k_lsd_grow<<<n, 32, 0, st>>>(img, (u32 *)ctx->lsd2.p, (const u32 *)ctx->lsd3.p, (u32 *)ctx->lsd4.p, cnt, P, segs,
+                                 width, prec_out, counts);
+    LE_T1(ctx, LE_K_LSD_GROW, st);
+    LE_LAUNCH_CHECK(ctx);
+    return LE_OK;
+}

@@ -1,0 +1,234 @@
+"""Batched, stream-asynchronous front door of the line engine (CUDA tensors in, CUDA tensors out).
+
+One ``Engine`` per (process, device).  torch supplies device memory, the current CUDA stream and
+(in ``dist.py``) the process group; every pixel of arithmetic happens in liblineengine.so.
+Variable-length results come back padded ``[N, max_k, ...]`` together with ``counts[N]``.
+"""
+import ctypes as C
+import math
+
+import torch
+
+from . import _native
+from ._native import lib
+
+
+class EngineError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"{_native.ERRORS.get(code, code)}: {msg}")
+        self.code = code
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+class Engine:
+    """Owns one ``le_ctx``.  Methods enqueue work on ``torch.cuda.current_stream(device)``."""
+
+    def __init__(self, device=None, max_h=0, max_w=0, max_batch=0):
+        if not torch.cuda.is_available():
+            raise RuntimeError("graphics_project_b200.Engine needs a CUDA device (no CPU fallback)")
+        self.device = torch.device("cuda", torch.cuda.current_device() if device is None else
+                                   (device if isinstance(device, int) else torch.device(device).index or 0))
+        ctx = C.c_void_p()
+        rc = lib.le_create(C.byref(ctx), self.device.index, max_h, max_w, max_batch)
+        if rc != 0:
+            raise EngineError(rc, lib.le_last_error(None).decode())
+        self._ctx = ctx
+
+    def close(self):
+        if getattr(self, "_ctx", None):
+            lib.le_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ helpers
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _ok(self, rc):
+        if rc != 0:
+            raise EngineError(rc, lib.le_last_error(self._ctx).decode())
+
+    def _img(self, t, channels):
+        if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.uint8):
+            raise TypeError("expected a CUDA uint8 tensor")
+        if channels == 3:
+            if t.dim() == 3:
+                t = t[None]
+            if t.dim() != 4 or t.shape[-1] != 3:
+                raise ValueError("expected [N,H,W,3]")
+        else:
+            if t.dim() == 2:
+                t = t[None]
+            if t.dim() != 3:
+                raise ValueError("expected [N,H,W]")
+        return t.contiguous()
+
+    def check(self):
+        """Synchronise and raise if a device-side queue overflowed."""
+        self._ok(lib.le_check(self._ctx, self._stream()))
+
+    @property
+    def launches(self):
+        return lib.le_launch_count(self._ctx)
+
+    def timing(self, on):
+        self._ok(lib.le_timing_enable(self._ctx, int(on)))
+
+    def timing_read(self):
+        """{kernel_name: (total_ms, launches)} since the last read (synchronises the recorded events)."""
+        out = {}
+        for k in range(10):
+            ms, cnt = C.c_double(), C.c_int()
+            self._ok(lib.le_timing_read(self._ctx, k, C.byref(ms), C.byref(cnt)))
+            if cnt.value:
+                out[lib.le_kernel_name(k).decode()] = (ms.value, cnt.value)
+        return out
+
+    @property
+    def workspace_bytes(self):
+        return lib.le_workspace_bytes(self._ctx)
+
+    # ------------------------------------------------------------------ a1-a4
+    def bgr2gray(self, bgr):
+        bgr = self._img(bgr, 3)
+        n, h, w, _ = bgr.shape
+        out = torch.empty((n, h, w), dtype=torch.uint8, device=self.device)
+        self._ok(lib.le_bgr2gray_u8(self._ctx, _ptr(bgr), _ptr(out), n, h, w, self._stream()))
+        return out
+
+    def gauss5(self, gray):
+        gray = self._img(gray, 1)
+        n, h, w = gray.shape
+        out = torch.empty_like(gray)
+        self._ok(lib.le_gauss5_u8(self._ctx, _ptr(gray), _ptr(out), n, h, w, self._stream()))
+        return out
+
+    def normalize_minmax(self, gray):
+        gray = self._img(gray, 1)
+        n, h, w = gray.shape
+        out = torch.empty_like(gray)
+        self._ok(lib.le_minmax_normalize_u8(self._ctx, _ptr(gray), _ptr(out), n, h, w, self._stream()))
+        return out
+
+    def canny(self, gray, lo, hi, out=None):
+        return self.front_canny(gray, lo, hi, blur=False, normalize=False, out=out)
+
+    def front_canny(self, src, lo, hi, blur=False, normalize=False, out=None):
+        """[BGR->gray] -> [blur5] -> [normalize] -> Canny.  ``src`` is [N,H,W,3] BGR or [N,H,W] gray."""
+        ch = 3 if src.dim() == 4 else 1  # a single BGR frame must be passed as [1,H,W,3]
+        src = self._img(src, ch)
+        n, h, w = src.shape[:3]
+        if out is None:
+            out = torch.empty((n, h, w), dtype=torch.uint8, device=self.device)
+        self._ok(lib.le_front_canny_u8(self._ctx, _ptr(src), ch, int(blur), int(normalize), _ptr(out), n, h, w,
+                                       float(lo), float(hi), self._stream()))
+        self._last_edges_shape = (n, h, w)
+        return out
+
+    # ------------------------------------------------------------------ a5
+    @staticmethod
+    def hough_dims(h, w, rho=1.0, theta=math.pi / 180):
+        na, nr = C.c_int(), C.c_int()
+        if lib.le_hough_dims(h, w, rho, theta, C.byref(na), C.byref(nr)) != 0:
+            raise ValueError("bad Hough parameters")
+        return na.value, nr.value
+
+    def hough_lines(self, edges, rho, theta, threshold, max_lines=4096, want_accum=False, want_votes=True,
+                    shape=None, out=None):
+        """``edges`` [N,H,W] u8 (non-zero = edge) or None to vote from the edge lists left by the last
+        ``front_canny`` (then ``shape`` defaults to that call's).  Returns (lines [N,max,2] f32,
+        votes [N,max] i32 or None, counts [N] i32, accum [N,na+2,nr+2] i32 or None)."""
+        if edges is None:
+            n, h, w = shape or self._last_edges_shape
+        else:
+            edges = self._img(edges, 1)
+            n, h, w = edges.shape
+        na, nr = self.hough_dims(h, w, rho, theta)
+        if out is not None:
+            lines, votes, counts, accum = out
+        else:
+            lines = torch.empty((n, max_lines, 2), dtype=torch.float32, device=self.device)
+            votes = torch.empty((n, max_lines), dtype=torch.int32, device=self.device) if want_votes else None
+            counts = torch.empty((n,), dtype=torch.int32, device=self.device)
+            accum = torch.empty((n, na + 2, nr + 2), dtype=torch.int32, device=self.device) if want_accum else None
+        self._ok(lib.le_hough_lines(self._ctx, _ptr(edges), n, h, w, float(rho), float(theta), int(threshold),
+                                    _ptr(accum), _ptr(lines), _ptr(votes), _ptr(counts), lines.shape[1],
+                                    self._stream()))
+        return lines, votes, counts, accum
+
+    # ------------------------------------------------------------------ a6
+    def hough_lines_p(self, edges, rho, theta, threshold, min_line_length=0, max_line_gap=0, max_segs=4096):
+        edges = self._img(edges, 1)
+        n, h, w = edges.shape
+        segs = torch.empty((n, max_segs, 4), dtype=torch.int32, device=self.device)
+        counts = torch.empty((n,), dtype=torch.int32, device=self.device)
+        self._ok(lib.le_hough_lines_p(self._ctx, _ptr(edges), n, h, w, float(rho), float(theta), int(threshold),
+                                      int(min_line_length), int(max_line_gap), _ptr(segs), _ptr(counts), max_segs,
+                                      self._stream()))
+        return segs, counts
+
+    # ------------------------------------------------------------------ a7
+    def lsd(self, gray, refine=0, scale=0.8, sigma_scale=0.6, quant=2.0, ang_th=22.5, log_eps=0.0, density_th=0.7,
+            n_bins=1024, max_segs=4096):
+        gray = self._img(gray, 1)
+        n, h, w = gray.shape
+        segs = torch.empty((n, max_segs, 4), dtype=torch.float32, device=self.device)
+        width = torch.empty((n, max_segs), dtype=torch.float64, device=self.device)
+        prec = torch.empty((n, max_segs), dtype=torch.float64, device=self.device)
+        counts = torch.empty((n,), dtype=torch.int32, device=self.device)
+        self._ok(lib.le_lsd(self._ctx, _ptr(gray), n, h, w, int(refine), float(scale), float(sigma_scale),
+                            float(quant), float(ang_th), float(log_eps), float(density_th), int(n_bins), _ptr(segs),
+                            _ptr(width), _ptr(prec), _ptr(counts), max_segs, self._stream()))
+        return segs, width, prec, counts
+
+    # ------------------------------------------------------------------ a9-a12
+    def segments_to_polar(self, segs):
+        segs = segs.to(self.device, torch.float64).contiguous().view(-1, 4)
+        out = torch.empty((segs.shape[0], 2), dtype=torch.float64, device=self.device)
+        if segs.shape[0]:
+            self._ok(lib.le_segments_to_polar(self._ctx, _ptr(segs), segs.shape[0], _ptr(out), self._stream()))
+        return out
+
+    def vp_loss(self, lines, cand, width=600.0, height=400.0):
+        lines = lines.to(self.device, torch.float64).contiguous().view(-1, 2)
+        cand = cand.to(self.device, torch.float64).contiguous().view(-1, 2)
+        out = torch.empty((cand.shape[0],), dtype=torch.float64, device=self.device)
+        self._ok(lib.le_vp_loss(self._ctx, _ptr(lines), lines.shape[0], _ptr(cand), cand.shape[0], float(width),
+                                float(height), _ptr(out), self._stream()))
+        return out
+
+    def vp_sphere_hist(self, segs, width=600.0, height=400.0, n_az=360, n_el=90):
+        segs = segs.to(self.device, torch.float64).contiguous().view(-1, 4)
+        hist = torch.empty((n_el, n_az), dtype=torch.int32, device=self.device)
+        self._ok(lib.le_vp_sphere_hist(self._ctx, _ptr(segs), segs.shape[0], float(width), float(height), _ptr(hist),
+                                       n_az, n_el, self._stream()))
+        return hist
+
+    def pair_intersections(self, lines, max_out=None):
+        lines = lines.to(self.device, torch.float32).contiguous().view(-1, 2)
+        m = lines.shape[0]
+        max_out = max(1, m * (m - 1) // 2 if max_out is None else max_out)
+        out = torch.empty((max_out, 2), dtype=torch.float64, device=self.device)
+        count = torch.zeros((1,), dtype=torch.int32, device=self.device)
+        self._ok(lib.le_pair_intersections(self._ctx, _ptr(lines), m, _ptr(out), _ptr(count), max_out,
+                                           self._stream()))
+        return out, count
+
+
+_default = {}
+
+
+def default_engine(device=None):
+    """Process-wide engine for the single-image numpy API (one per device)."""
+    idx = torch.cuda.current_device() if device is None else int(device)
+    if idx not in _default:
+        _default[idx] = Engine(idx)
+    return _default[idx]

@@ -1,0 +1,186 @@
+"""Vanishing-point fit with the reference's signatures (opencv_fit_color.py, opencv_renewed.py:16-32).
+
+The reference's ``regress_lines`` is an unseeded random search: 1500 Python evaluations of
+``sum_loss`` (~1 s for 75 lines).  Here the same loss is evaluated for whole candidate sets on the
+GPU (``le_vp_loss``): a dense deterministic grid over the reference's search domain
+(phi in [0,pi), theta in [0,pi/2)), seeds from the Gaussian-sphere histogram of pairwise
+interpretation-plane intersections (``le_vp_sphere_hist``), then shrinking refinement grids around
+the best candidate.  Returned values keep the reference's types: ``((phi, theta), loss)``.
+"""
+import numpy as np
+import torch
+
+from .engine import default_engine
+from . import detectors
+
+HEIGHT = 400
+WIDTH = 600
+
+
+def edges_to_polar_lines(edges):
+    """opencv_renewed.py:16-17: list of (a, b) endpoint pairs -> (N, 2) array of (rho, phi)."""
+    if len(edges) == 0:
+        return np.zeros((0,), np.float64)  # np.array([]) in the reference
+    segs = np.array([[a[0], a[1], b[0], b[1]] for a, b in edges], dtype=np.float64)
+    eng = default_engine()
+    return eng.segments_to_polar(torch.from_numpy(segs)).cpu().numpy()
+
+
+def get_focal_points(phi, theta, width=WIDTH, height=HEIGHT):
+    """opencv_fit_color.py:95-101 (scalar; three vanishing points in pixels)."""
+    sc_points = [(1 / (np.tan(theta) * np.sin(phi)), 1 / np.tan(phi)),
+                 (0, -np.tan(phi)),
+                 (-np.tan(theta) / np.sin(phi), 1 / np.tan(phi))]
+    return [np.array([height / 2 * p[0] + width / 2, height / 2 * p[1] + height / 2]) for p in sc_points]
+
+
+def loss_function(point, rho, phi):
+    """opencv_fit_color.py:14-15."""
+    return pow(point[1] * np.sin(phi) + point[0] * np.cos(phi) - rho, 2)
+
+
+def losses(lines, candidates, width=WIDTH, height=HEIGHT):
+    """sum_loss for every (phi, theta) row of ``candidates`` -> float64 array (GPU)."""
+    eng = default_engine()
+    lines_t = torch.as_tensor(np.asarray(lines, dtype=np.float64))
+    cand_t = torch.as_tensor(np.asarray(candidates, dtype=np.float64))
+    return eng.vp_loss(lines_t, cand_t, width, height).cpu().numpy()
+
+
+def sum_loss(phi, theta, lines, width=WIDTH, height=HEIGHT):
+    """opencv_fit_color.py:25-26."""
+    return float(losses(lines, [[phi, theta]], width, height)[0])
+
+
+def sphere_seeds(lines, width=WIDTH, height=HEIGHT, n_az=360, n_el=90, top=8):
+    """(phi, theta) hypotheses from the Gaussian-sphere histogram peaks.
+
+    A polar line x cos(phi) + y sin(phi) = rho is turned back into two pixel points; the histogram
+    votes every pairwise intersection direction v (folded to v_z >= 0).  A peak direction is read as
+    the 'x' or the 'z' vanishing point of get_focal_points: d_x = (1/(tan t sin p), 1/tan p, 1),
+    d_z = (-tan t / sin p, 1/tan p, 1)."""
+    lines = np.asarray(lines, dtype=np.float64).reshape(-1, 2)
+    if len(lines) < 2:
+        return np.zeros((0, 2))
+    rho, phi = lines[:, 0], lines[:, 1]
+    p0 = np.stack([rho * np.cos(phi), rho * np.sin(phi)], 1)
+    d = np.stack([-np.sin(phi), np.cos(phi)], 1) * 100.0
+    segs = np.concatenate([p0 - d, p0 + d], 1)
+    eng = default_engine()
+    hist = eng.vp_sphere_hist(torch.from_numpy(segs), width, height, n_az, n_el)
+    flat = hist.flatten()
+    k = min(top, flat.numel())
+    idx = torch.topk(flat, k).indices.cpu().numpy()
+    seeds = []
+    for i in idx:
+        be, ba = divmod(int(i), n_az)
+        az = (ba + 0.5) / n_az * 2 * np.pi - np.pi
+        el = (be + 0.5) / n_el * (np.pi / 2)
+        vx, vy, vz = np.cos(el) * np.cos(az), np.cos(el) * np.sin(az), np.sin(el)
+        if vz < 1e-6:
+            continue
+        x, y = vx / vz, vy / vz
+        ph = np.arctan2(1.0, y) % np.pi  # 1/tan(phi) = y
+        if abs(x) < 1e-9 or abs(np.sin(ph)) < 1e-9:
+            continue
+        th_x = np.arctan(1.0 / (x * np.sin(ph)))   # x = 1/(tan t sin p)
+        th_z = np.arctan(-x * np.sin(ph))          # x = -tan t / sin p
+        for th in (th_x, th_z):
+            if 0 <= th < np.pi / 2:
+                seeds.append((ph, th))
+    return np.array(seeds).reshape(-1, 2)
+
+
+def _grid(phi_lo, phi_hi, th_lo, th_hi, n_phi, n_th):
+    ph = phi_lo + (np.arange(n_phi) + 0.5) / n_phi * (phi_hi - phi_lo)
+    th = th_lo + (np.arange(n_th) + 0.5) / n_th * (th_hi - th_lo)
+    return np.stack(np.meshgrid(ph, th, indexing="ij"), -1).reshape(-1, 2)
+
+
+def regress_lines(lines, iterations=500, refinement_iterations=100, refinement_area=0.3, width=WIDTH,
+                  height=HEIGHT, verbose=True):
+    """opencv_fit_color.py:28-47 signature and return type; deterministic GPU search.
+
+    ``iterations`` / ``refinement_iterations`` are lower bounds on the number of candidates per phase."""
+    lines = np.asarray(lines, dtype=np.float64).reshape(-1, 2)
+    best_loss = 100000
+    best = (0, 0)
+    if len(lines) == 0:
+        raise ZeroDivisionError("division by zero")  # min_loss divides by len(lines) in the reference
+    n_phi = max(192, int(np.ceil(np.sqrt(2 * max(iterations, 1)))))
+    cand = _grid(0, np.pi, 0, np.pi / 2, n_phi, max(96, n_phi // 2))
+    seeds = sphere_seeds(lines, width, height)
+    if len(seeds):
+        cand = np.concatenate([cand, seeds])
+    ls = losses(lines, cand, width, height)
+    ls = np.where(np.isnan(ls), np.inf, ls)
+    i = int(np.argmin(ls))
+    if ls[i] < best_loss:
+        best_loss, best = float(ls[i]), (float(cand[i, 0]), float(cand[i, 1]))
+    side = float(refinement_area)
+    n_ref = max(32, int(np.ceil(np.sqrt(max(refinement_iterations, 1)))))
+    for _ in range(4):  # reference does one refinement pass; extra passes only shrink the box
+        cphi, cth = best
+        cand = _grid(cphi - side / 2, cphi + side / 2, cth - side / 2, cth + side / 2, n_ref, n_ref)
+        ls = losses(lines, cand, width, height)
+        ls = np.where(np.isnan(ls), np.inf, ls)
+        i = int(np.argmin(ls))
+        if ls[i] < best_loss:
+            best_loss, best = float(ls[i]), (float(cand[i, 0]), float(cand[i, 1]))
+        side *= 4.0 / n_ref
+    if verbose:
+        print(" The loss is ", best_loss)
+    return best, best_loss
+
+
+def which_line(focal_points, line, threshold=700):
+    """opencv_fit_color.py:49-59."""
+    x_loss, y_loss, z_loss = (loss_function(focal_points[0], *line), loss_function(focal_points[1], *line),
+                              loss_function(focal_points[2], *line))
+    if min([x_loss, y_loss, z_loss]) >= threshold:
+        return None
+    if x_loss <= y_loss and x_loss <= z_loss:
+        return "x"
+    elif y_loss <= x_loss and y_loss <= z_loss:
+        return "y"
+    else:
+        return "z"
+
+
+def classifyEdges(edges, threshold_multiplier=1.2):
+    """opencv_renewed.py:19-32."""
+    lines = edges_to_polar_lines(edges)
+    phi_theta, loss = regress_lines(lines, iterations=1000, refinement_iterations=500,
+                                    refinement_area=np.deg2rad(15))
+    phi, theta = phi_theta
+    focal_points = get_focal_points(phi, theta)
+    pairs = [(edge, which_line(focal_points, line, threshold=loss * threshold_multiplier))
+             for edge, line in zip(edges, lines)]
+    x_edges = [line for line, which in pairs if which == "x"]
+    y_edges = [line for line, which in pairs if which == "y"]
+    z_edges = [line for line, which in pairs if which == "z"]
+    return x_edges, y_edges, z_edges, phi, theta
+
+
+def get_camera_angles(image, iterations=1000, method="hough", refinement_iterations=500):
+    """opencv_fit_color.py:71-93."""
+    if method == "hough":
+        eng, t = detectors._bgr_dev(image)
+        eng.front_canny(t, 5, 10, blur=True, normalize=False)
+        cap = 4096
+        while True:
+            ln, _, counts, _ = eng.hough_lines(None, 1, np.pi / 180, 50, max_lines=cap)
+            n = int(counts[0].item())
+            if n <= cap:
+                break
+            cap = n
+        if n == 0:
+            raise TypeError("'NoneType' object is not subscriptable")  # lines[:,0,:] on None in the reference
+        lines = ln[0, :n].cpu().numpy()
+    elif method == "lsd":
+        pairs = detectors.lsd(image)
+        pairs = [(a, b) for a, b in pairs if np.linalg.norm(b - a) > 10]
+        lines = edges_to_polar_lines(pairs)
+    else:
+        return None
+    return regress_lines(lines, iterations=iterations, refinement_iterations=refinement_iterations)[0]
