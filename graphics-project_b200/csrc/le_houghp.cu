@@ -6,7 +6,7 @@
 // 180-angle vote of a pick is one parallel step with NO atomics (a row has a single writer) and
 // the arg-max is a block reduction; (3) the line walk: a warp evaluates 32 steps of the Q16
 // fixed-point walk at once and resolves the gap rule with ballots.
-// The accumulator keeps only the rho support of each angle (u16 [numangle][stride], ~0.8 MB at
+// The accumulator keeps only the rho support of each angle (s16 [numangle][stride], ~0.8 MB at
 // 1080p instead of cv2's 4.3 MB int32) so the working set of all resident frames stays in L2.
 #include "le_common.cuh"
 
@@ -92,6 +92,7 @@ struct PPShared {
     int end_xy[2][2];
     int pick[2];
     int nlines;
+    int ntrace;
 };
 
 static __device__ __forceinline__ u32 rng_next(u64 &st)
@@ -101,16 +102,16 @@ static __device__ __forceinline__ u32 rng_next(u64 &st)
 }
 
 __global__ void __launch_bounds__(PP_THREADS)
-k_ppht(u8 *__restrict__ mask, u32 *__restrict__ nz_g, u16 *__restrict__ accum, const float *__restrict__ trig,
+k_ppht(u8 *__restrict__ mask, u32 *__restrict__ nz_g, short *__restrict__ accum, const float *__restrict__ trig,
        int *__restrict__ counters, int32_t *__restrict__ segs, int32_t *__restrict__ counts, int max_segs, int h,
-       int w, int numangle, int stride, int threshold, int line_length, int line_gap)
+       int w, int numangle, int stride, int threshold, int line_length, int line_gap, int32_t *trace, int trace_cap)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     PPShared &S = *reinterpret_cast<PPShared *>(smem_raw);
     const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const size_t npx = (size_t)h * w;
     u8 *mk = mask + (size_t)f * npx;
-    u16 *acc = accum + (size_t)f * numangle * stride;
+    short *acc = accum + (size_t)f * numangle * stride;  // signed: un-voting never-voted pixels goes negative (as in cv2)
     int count = counters[f * LE_C_STRIDE + LE_C_AUX0];
     const int *rlo_g = (const int *)(trig + 2 * numangle);
     // nz list: shared when it fits
@@ -119,7 +120,7 @@ k_ppht(u8 *__restrict__ mask, u32 *__restrict__ nz_g, u16 *__restrict__ accum, c
         for (int i = tid; i < count; i += PP_THREADS) S.nz[i] = nz[i];
         nz = S.nz;
     }
-    if (tid == 0) S.nlines = 0;
+    if (tid == 0) { S.nlines = 0; S.ntrace = 0; }
     // angle owned by this thread (generic numangle handled by a strided loop; 180 -> one each)
     const bool single = numangle <= PP_THREADS;
     float tc = 0.f, ts = 0.f;
@@ -157,18 +158,18 @@ k_ppht(u8 *__restrict__ mask, u32 *__restrict__ nz_g, u16 *__restrict__ accum, c
         if (single) {
             if (tid < numangle) {
                 int r = __float2int_rn(__fadd_rn(__fmul_rn((float)j, tc), __fmul_rn((float)i, ts)));
-                u16 *cell = acc + (size_t)tid * stride + (r - rlo);
+                short *cell = acc + (size_t)tid * stride + (r - rlo);
                 int val = *cell + 1;
-                *cell = (u16)val;
-                best = ((unsigned long long)val << 32) | (u32)(0x7fffffff - tid);
+                *cell = (short)val;
+                best = ((unsigned long long)(u32)(val + 0x8000) << 32) | (u32)(0x7fffffff - tid);
             }
         } else {
             for (int n = tid; n < numangle; n += PP_THREADS) {
                 int r = __float2int_rn(__fadd_rn(__fmul_rn((float)j, trig[n]), __fmul_rn((float)i, trig[numangle + n])));
-                u16 *cell = acc + (size_t)n * stride + (r - rlo_g[n]);
+                short *cell = acc + (size_t)n * stride + (r - rlo_g[n]);
                 int val = *cell + 1;
-                *cell = (u16)val;
-                unsigned long long key = ((unsigned long long)val << 32) | (u32)(0x7fffffff - n);
+                *cell = (short)val;
+                unsigned long long key = ((unsigned long long)(u32)(val + 0x8000) << 32) | (u32)(0x7fffffff - n);
                 best = key > best ? key : best;
             }
         }
@@ -181,7 +182,7 @@ k_ppht(u8 *__restrict__ mask, u32 *__restrict__ nz_g, u16 *__restrict__ accum, c
         best = S.red[0];
 #pragma unroll
         for (int k = 1; k < PP_THREADS / 32; k++) best = S.red[k] > best ? S.red[k] : best;
-        const int max_val = (int)(best >> 32);
+        const int max_val = (int)(best >> 32) - 0x8000;  // biased so that negative cells order correctly
         const int max_n = 0x7fffffff - (int)(u32)best;
         if (max_val < threshold) continue;  // uniform (needs no barrier: S.red is rewritten only after the next sync)
         // ---- walk set-up (all threads, identical)
@@ -237,6 +238,14 @@ k_ppht(u8 *__restrict__ mask, u32 *__restrict__ nz_g, u16 *__restrict__ accum, c
         __syncthreads();
         const int e0x = S.end_xy[0][0], e0y = S.end_xy[0][1], e1x = S.end_xy[1][0], e1y = S.end_xy[1][1];
         const bool good = abs(e1x - e0x) >= line_length || abs(e1y - e0y) >= line_length;
+        if (trace && f == 0 && tid == 0) {
+            int tp = S.ntrace++;
+            if (tp < trace_cap) {
+                int32_t *o = trace + tp * 10;
+                o[0] = j; o[1] = i; o[2] = max_val; o[3] = max_n; o[4] = e0x; o[5] = e0y; o[6] = e1x; o[7] = e1y;
+                o[8] = good; o[9] = dx0 * 4 + dy0 % 4;
+            }
+        }
         // ---- second walk: clear the mask; un-vote if the segment is accepted
         for (int k = 0; k < 2; k++) {
             const int dx = k ? -dx0 : dx0, dy = k ? -dy0 : dy0;
@@ -281,6 +290,15 @@ k_ppht(u8 *__restrict__ mask, u32 *__restrict__ nz_g, u16 *__restrict__ accum, c
     if (tid == 0) counts[f] = S.nlines;
 }
 
+// debug hook (tests only): record the voting picks of frame 0 -> 10 ints each
+static int32_t *g_ppht_trace = nullptr;
+static int g_ppht_trace_cap = 0;
+extern "C" void le_debug_ppht_trace(int32_t *dev_buf, int cap)
+{
+    g_ppht_trace = dev_buf;
+    g_ppht_trace_cap = cap;
+}
+
 extern "C" int le_hough_lines_p(le_ctx *ctx, const uint8_t *edges, int n, int h, int w, double rho, double theta,
                                 int threshold, int min_line_length, int max_line_gap, int32_t *segs,
                                 int32_t *counts, int max_segs, void *stream)
@@ -321,9 +339,9 @@ extern "C" int le_hough_lines_p(le_ctx *ctx, const uint8_t *edges, int n, int h,
     }
     LE_T0(ctx, LE_K_PPHT, st);
     k_ppht<<<n, PP_THREADS, sizeof(PPShared), st>>>((u8 *)ctx->ppht_mask.p, (u32 *)ctx->ppht_nz.p,
-                                                    (u16 *)ctx->ppht_accum.p, (const float *)ctx->trig.p,
+                                                    (short *)ctx->ppht_accum.p, (const float *)ctx->trig.p,
                                                     (int *)ctx->counters.p, segs, counts, max_segs, h, w, numangle,
-                                                    stride, threshold, min_line_length, max_line_gap);
+                                                    stride, threshold, min_line_length, max_line_gap, g_ppht_trace, g_ppht_trace_cap);
     LE_T1(ctx, LE_K_PPHT, st);
     LE_LAUNCH_CHECK(ctx);
     return LE_OK;

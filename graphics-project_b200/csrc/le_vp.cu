@@ -99,7 +99,7 @@ static __device__ __forceinline__ bool pair_ok(const float *__restrict__ lines, 
     if ((dr < 40.0 && dt < d10) || dt > d80) return false;
     // np.linalg.solve raises on an exactly singular matrix (identical angles): skipped by the reference
     double c1 = cos((double)t1), s1 = sin((double)t1), c2 = cos((double)t2), s2 = sin((double)t2);
-    return c1 * s2 - c2 * s1 != 0.0;
+    return __dsub_rn(__dmul_rn(c1, s2), __dmul_rn(c2, s1)) != 0.0;  // unfused: identical angles give exactly 0
 }
 __global__ void k_pair_count(const float *__restrict__ lines, int m, int *__restrict__ rowcnt)
 {

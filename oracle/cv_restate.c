@@ -262,6 +262,11 @@ static inline unsigned rng_next(uint64_t *st)
     return (unsigned)*st;
 }
 
+static int *g_pp_trace = 0;
+static int g_pp_trace_cap = 0, g_pp_trace_n = 0;
+void or_ppht_trace(int *buf, int cap) { g_pp_trace = buf; g_pp_trace_cap = cap; g_pp_trace_n = 0; }
+int or_ppht_trace_count(void) { return g_pp_trace_n; }
+
 int or_hough_lines_p(const u8 *edges, int h, int w, float rho, float theta, int threshold,
                      int line_length, int line_gap, int *segs, int max_segs)
 {
@@ -333,6 +338,11 @@ int or_hough_lines_p(const u8 *edges, int h, int w, float rho, float theta, int 
         }
         good_line = abs(line_end[1][0] - line_end[0][0]) >= line_length ||
                     abs(line_end[1][1] - line_end[0][1]) >= line_length;
+        if (g_pp_trace && g_pp_trace_n < g_pp_trace_cap) {
+            int *o = g_pp_trace + 10 * g_pp_trace_n++;
+            o[0] = j; o[1] = i; o[2] = max_val; o[3] = max_n; o[4] = line_end[0][0]; o[5] = line_end[0][1];
+            o[6] = line_end[1][0]; o[7] = line_end[1][1]; o[8] = good_line; o[9] = dx0 * 4 + dy0 % 4;
+        }
         for (k = 0; k < 2; k++) {
             int x = x0, y = y0, dx = dx0, dy = dy0;
             if (k > 0) { dx = -dx; dy = -dy; }

@@ -14,7 +14,7 @@ def dev(a):
     return torch.from_numpy(np.ascontiguousarray(a)).cuda()
 
 
-def run_hough(engine, edges_np, thr, rho=1.0, theta=np.pi / 180, cap=1 << 15):
+def run_hough(engine, edges_np, thr, rho=1.0, theta=np.pi / 180, cap=1 << 16):
     lines, votes, counts, accum = engine.hough_lines(dev(edges_np)[None], rho, theta, thr, max_lines=cap,
                                                      want_accum=True)
     n = int(counts[0])

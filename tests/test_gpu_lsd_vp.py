@@ -131,6 +131,10 @@ def test_pair_intersections_match_reference(engine, golden_vp):
     from graphics_project_b200 import detectors
     got = np.array(detectors._getIntersections(golden_vp["intersections_in"].reshape(-1, 1, 2))).reshape(-1, 2)
     ref = golden_vp["intersections_out"]
+    # Pairs with IDENTICAL angles are singular: np.linalg.solve raises and the reference skips them
+    # (opencv.py:184-188), except when LAPACK's float32 LU misses the singularity (theta == pi/2 here)
+    # and returns garbage around 1e25.  The engine skips every identical-angle pair.
+    ref = ref[np.abs(ref).max(axis=1) < 1e12]
     assert got.shape == ref.shape
     assert np.allclose(got, ref, rtol=1e-3, atol=5e-2)  # the reference solves in float32
 
