@@ -5,6 +5,10 @@
 // candidates (back).  One pass over the input produces the NMS classification, hysteresis then
 // runs on the sparse queue only.
 #include "le_common.cuh"
+#include <stdlib.h>
+
+int le_front_rows_launch(le_ctx *ctx, const u8 *src, int ch, int blur, int lut, u8 *edges, int n, int h, int w, int lo,
+                         int hi, cudaStream_t st);
 
 // ------------------------------------------------------------------ standalone stages
 __global__ void k_bgr2gray(const u8 *__restrict__ bgr, u8 *__restrict__ gray, size_t npx)
@@ -521,11 +525,15 @@ int le_front_launch(le_ctx *ctx, const u8 *src, int ch, int do_blur, int do_norm
     }
     k_zero_counters<<<(n * LE_C_STRIDE + 255) / 256, 256, 0, st>>>((int *)ctx->counters.p, n);
     LE_LAUNCH_CHECK(ctx);
-    if (do_norm) rc = launch_front_t<false, false, true>(ctx, in, edges, n, h, w, lo, hi, st);
-    else if (in_ch == 3 && blur) rc = launch_front_t<true, true, false>(ctx, in, edges, n, h, w, lo, hi, st);
-    else if (in_ch == 3) rc = launch_front_t<true, false, false>(ctx, in, edges, n, h, w, lo, hi, st);
-    else if (blur) rc = launch_front_t<false, true, false>(ctx, in, edges, n, h, w, lo, hi, st);
-    else rc = launch_front_t<false, false, false>(ctx, in, edges, n, h, w, lo, hi, st);
+    if (getenv("LE_FRONT_V1")) {  // previous shared-memory tile kernel, kept for A/B measurements only
+        if (do_norm) rc = launch_front_t<false, false, true>(ctx, in, edges, n, h, w, lo, hi, st);
+        else if (in_ch == 3 && blur) rc = launch_front_t<true, true, false>(ctx, in, edges, n, h, w, lo, hi, st);
+        else if (in_ch == 3) rc = launch_front_t<true, false, false>(ctx, in, edges, n, h, w, lo, hi, st);
+        else if (blur) rc = launch_front_t<false, true, false>(ctx, in, edges, n, h, w, lo, hi, st);
+        else rc = launch_front_t<false, false, false>(ctx, in, edges, n, h, w, lo, hi, st);
+    } else {
+        rc = le_front_rows_launch(ctx, in, in_ch, blur, do_norm, edges, n, h, w, lo, hi, st);
+    }
     if (rc) return rc;
     LE_T0(ctx, LE_K_HYST, st);
     k_hysteresis<<<n, 1024, 0, st>>>(edges, (u32 *)ctx->queue.p, (int *)ctx->counters.p, h, w);
