@@ -3,12 +3,14 @@
 // One WARP owns a column strip of 128 pixels (lane = 4 consecutive pixels = one packed word) and
 // walks DOWN the rows of a segment, keeping every vertical window (5 gray rows, 3 blurred rows,
 // 3 magnitude rows) in registers as transposed-FIR partial sums of packed 16-bit pairs.  Horizontal
-// neighbours come from the adjacent lanes with warp shuffles, so there is no shared memory, no
-// block barrier and every input byte is loaded from HBM exactly once per strip (the 8-pixel strip
-// overlap and the 8 halo rows per segment hit L2).  The arithmetic is packed: IDP.2A for the Q15
-// gray conversion, PRMT byte windows, 2x16-bit IMAD/IADD3 for the [1 4 6 4 1] and Sobel sums,
-// VIMNMX.U16x2 for |gx|+|gy|.  The direction-dependent NMS test is scalar but only runs for warp
-// rows that contain a pixel with magnitude > low threshold (edges are sparse: <3 % of warp rows).
+// neighbours come from the adjacent lanes with warp shuffles: no block barrier, and every input
+// byte is fetched from HBM once per strip (the 8-pixel strip overlap and the 8 halo rows per
+// segment hit L2).  Input rows are streamed through a per-warp shared-memory ring with cp.async
+// (LDGSTS), 7 rows ahead, so the bytes in flight per SM do not depend on registers or occupancy.
+// The arithmetic is packed: IDP.2A for the Q15 gray conversion, PRMT byte windows, 2x16-bit
+// IMAD/IADD3 for the [1 4 6 4 1] and Sobel sums, VIMNMX.U16x2 for |gx|+|gy|.  The direction-
+// dependent NMS test is scalar and out of line; it only runs for warp rows that contain a pixel
+// with magnitude > low threshold (edges are sparse).
 //
 // Lane l of a strip covers x in [xs + 4l, xs + 4l + 3], xs = 120 * strip - 4; lanes 1..30 produce
 // output, lanes 0 and 31 only provide the +-4 pixel halo (blur 2 + Sobel 1 + NMS 1).
@@ -16,6 +18,13 @@
 
 #define FR_STRIP 120
 #define FR_WARPS 4
+#define FR_DEPTH 8  // rows in the cp.async ring (prefetch distance FR_DEPTH - 1)
+#ifndef FR_MINBLK
+#define FR_MINBLK 8
+#endif
+#ifndef FR_UNROLL
+#define FR_UNROLL 2
+#endif
 
 static __device__ __forceinline__ u32 prmt(u32 a, u32 b, u32 s) { return __byte_perm(a, b, s); }
 
@@ -44,6 +53,14 @@ static __device__ __forceinline__ u32 load_px(const u8 *__restrict__ s, int y, i
     return s[(size_t)y * w + x];
 }
 
+static __device__ __forceinline__ void cp_async4(u32 smem_addr, const void *g)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_addr), "l"(g) : "memory");
+}
+static __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+static __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 struct FrontArgs {
     const u8 *src;
     u8 *map;
@@ -54,47 +71,108 @@ struct FrontArgs {
     int rows_per_seg, nstrips, nsegs;
 };
 
-// push helpers: strong pixels at the front of the frame queue, weak candidates at the back
-static __device__ __forceinline__ void push_list(bool pred, u32 value, int *counter, u32 *q, long long stride_sign,
-                                                 size_t base_index, int lane)
+// Pipeline state of one lane (packed 16-bit pairs: l = pixels 0,1; h = pixels 2,3)
+struct FrontState {
+    u32 a1l, a2l, a3l, a4l, a1h, a2h, a3h, a4h;  // vertical blur, transposed FIR partial sums
+    u32 s1l, s2l, ppl, s1h, s2h, pph;            // vertical Sobel
+    u32 gxl, gxh, gyl, gyh;                      // biased gradient (+1024) of the NMS row
+    u32 mul, muh, mml, mmh;                      // magnitude rows yo-1 (up) and yo (mid)
+    bool has_mid;
+};
+
+// Out-of-line NMS + double threshold for the 4 pixels of a lane.  Called warp-convergently.
+// Returns the map word (0 / 1 weak / 255 strong per byte).
+static __device__ __noinline__ u32 nms_slow(u32 mul, u32 muh, u32 mml, u32 mmh, u32 mdl, u32 mdh, u32 gxl, u32 gxh,
+                                            u32 gyl, u32 gyh, int has_mid, int lo, int hi)
 {
-    u32 b = __ballot_sync(~0u, pred);
-    if (b) {
-        int base = 0;
-        if (lane == (__ffs(b) - 1)) base = atomicAdd(counter, __popc(b));
-        base = __shfl_sync(~0u, base, __ffs(b) - 1);
-        if (pred) {
-            long long pos = (long long)base + __popc(b & ((1u << lane) - 1));
-            q[(long long)base_index + stride_sign * pos] = value;
+    // neighbours' magnitudes of pixel -1 (lane-1, its pixel 3) and pixel 4 (lane+1, its pixel 0)
+    u32 l_um = __shfl_up_sync(~0u, prmt(muh, mmh, 0x7632), 1);    // lo16 = up(-1), hi16 = mid(-1)
+    u32 l_dn = __shfl_up_sync(~0u, mdh >> 16, 1);                  // down(-1)
+    u32 r_um = __shfl_down_sync(~0u, prmt(mul, mml, 0x5410), 1);  // lo16 = up(4), hi16 = mid(4)
+    u32 r_dn = __shfl_down_sync(~0u, mdl & 0xffffu, 1);            // down(4)
+    u32 outw = 0;
+    if (has_mid) {
+        int up[6], mid[6], dn[6];
+        up[0] = l_um & 0xffff; mid[0] = l_um >> 16; dn[0] = l_dn;
+        up[1] = mul & 0xffff; up[2] = mul >> 16; up[3] = muh & 0xffff; up[4] = muh >> 16;
+        mid[1] = mml & 0xffff; mid[2] = mml >> 16; mid[3] = mmh & 0xffff; mid[4] = mmh >> 16;
+        dn[1] = mdl & 0xffff; dn[2] = mdl >> 16; dn[3] = mdh & 0xffff; dn[4] = mdh >> 16;
+        up[5] = r_um & 0xffff; mid[5] = r_um >> 16; dn[5] = r_dn;
+        int gx[4] = {(int)(gxl & 0xffff) - 1024, (int)(gxl >> 16) - 1024, (int)(gxh & 0xffff) - 1024,
+                     (int)(gxh >> 16) - 1024};
+        int gy[4] = {(int)(gyl & 0xffff) - 1024, (int)(gyl >> 16) - 1024, (int)(gyh & 0xffff) - 1024,
+                     (int)(gyh >> 16) - 1024};
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int mv = mid[k + 1];
+            if (mv > lo) {
+                int ax = abs(gx[k]), ay = abs(gy[k]) << 15;
+                int tg22x = ax * 13573;
+                bool keep;
+                if (ay < tg22x) keep = mv > mid[k] && mv >= mid[k + 2];
+                else {
+                    int tg67x = tg22x + (ax << 16);
+                    if (ay > tg67x) keep = mv > up[k + 1] && mv >= dn[k + 1];
+                    else if ((gx[k] ^ gy[k]) < 0) keep = mv > up[k + 2] && mv > dn[k];
+                    else keep = mv > up[k] && mv > dn[k + 2];
+                }
+                if (keep) outw |= (mv > hi ? 255u : 1u) << (8 * k);
+            }
+        }
+    }
+    return outw;
+}
+
+// strong pixels go to the front of the frame queue, weak candidates to the back (warp-aggregated)
+static __device__ __noinline__ void push_out(u32 outw, u32 pidx0, int *cnt, u32 *q, long long npx)
+{
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        u32 c = (outw >> (8 * k)) & 255u;
+#pragma unroll
+        for (int pass = 0; pass < 2; pass++) {
+            bool pred = pass == 0 ? (c == 255u) : (c == 1u);
+            u32 b = __ballot_sync(~0u, pred);
+            if (b) {
+                int leader = __ffs(b) - 1, base = 0;
+                if (lane == leader) base = atomicAdd(&cnt[pass == 0 ? LE_C_QTAIL : LE_C_WEAK], __popc(b));
+                base = __shfl_sync(~0u, base, leader);
+                if (pred) {
+                    long long pos = (long long)base + __popc(b & ((1u << lane) - 1));
+                    q[pass == 0 ? pos : npx - 1 - pos] = pidx0 + k;
+                }
+            }
         }
     }
 }
 
 template <bool BGR, bool BLUR, bool LUT>
-__global__ void __launch_bounds__(FR_WARPS * 32) k_front_rows(FrontArgs A)
+__global__ void __launch_bounds__(FR_WARPS * 32, FR_MINBLK) k_front_rows(FrontArgs A)
 {
     __shared__ u8 s_lut[LUT ? 256 : 4];
-    const int lane = threadIdx.x & 31;
+    __shared__ __align__(16) u32 s_ring[FR_WARPS][FR_DEPTH][BGR ? 96 : 32];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     if (LUT) {
         for (int i = threadIdx.x; i < 256; i += FR_WARPS * 32) s_lut[i] = A.lut[blockIdx.y * 256 + i];
         __syncthreads();
     }
     // work item of this warp: (frame f = blockIdx.y, segment, strip)
     const int f = blockIdx.y;
-    const int wi = blockIdx.x * FR_WARPS + (threadIdx.x >> 5);
+    const int wi = blockIdx.x * FR_WARPS + wib;
     if (wi >= A.nstrips * A.nsegs) return;
     const int strip = wi % A.nstrips, seg = wi / A.nstrips;
     const int h = A.h, w = A.w, lo = A.lo, hi = A.hi;
-    const size_t npx = (size_t)h * w;
+    const long long npx = (long long)h * w;
     const u8 *__restrict__ src = A.src + (size_t)f * npx * (BGR ? 3 : 1);
     u8 *__restrict__ map = A.map + (size_t)f * npx;
     u32 *q = A.queue + (size_t)f * npx;
     int *cnt = A.counters + f * LE_C_STRIDE;
 
     const int ys = seg * A.rows_per_seg, ye = min(h, ys + A.rows_per_seg);
-    const int x_lane = strip * FR_STRIP - 4 + 4 * lane;         // first pixel of this lane's word
-    const bool inside = x_lane >= 0 && x_lane + 3 < w;          // whole word inside the image
-    const bool fast_rows = BGR ? ((w * 3) & 3) == 0 : (w & 3) == 0;
+    const int x_lane = strip * FR_STRIP - 4 + 4 * lane;  // first pixel of this lane's word
+    const bool inside = x_lane >= 0 && x_lane + 3 < w;   // whole word inside the image
+    const bool fast_rows = (w & 3) == 0;                 // rows are word aligned (BGR: 3w % 4 == 0 too)
     const bool out_lane = lane >= 1 && lane <= 30 && x_lane < w;
     constexpr int LAGB = BLUR ? 2 : 0;
 
@@ -103,10 +181,9 @@ __global__ void __launch_bounds__(FR_WARPS * 32) k_front_rows(FrontArgs A)
     int fix_src = lane;
     bool need_fix = false;
     if (BLUR) {
-        if (x_lane + 3 < 0) { fix_sel = 0x4444; fix_src = lane + 1; }                    // all bytes := B(0)
-        else if (x_lane < 0) { fix_sel = 0x3210; }                                        // (cannot happen: x_lane % 4 == 0)
+        if (x_lane + 3 < 0) { fix_sel = 0x4444; fix_src = lane + 1; }  // all bytes := B(0)
         else if (x_lane >= w) { fix_sel = ((w & 3) == 0) ? 0x7777 : 0x3210; fix_src = lane - 1; }
-        else if (x_lane + 3 >= w) {                                                       // word contains W-1 at byte k
+        else if (x_lane + 3 >= w) {  // word contains W-1 at byte k < 3
             int k = w - 1 - x_lane;
             fix_sel = k == 0 ? 0x0000 : (k == 1 ? 0x1110 : 0x2210);
         }
@@ -114,50 +191,38 @@ __global__ void __launch_bounds__(FR_WARPS * 32) k_front_rows(FrontArgs A)
         need_fix = __any_sync(~0u, fix_sel != 0x3210);
     }
     // magnitude is 0 outside the image (per 16-bit half)
-    u32 mmask01 = ((x_lane >= 0 && x_lane < w) ? 0xffffu : 0u) | ((x_lane + 1 >= 0 && x_lane + 1 < w) ? 0xffff0000u : 0u);
-    u32 mmask23 = ((x_lane + 2 >= 0 && x_lane + 2 < w) ? 0xffffu : 0u) | ((x_lane + 3 >= 0 && x_lane + 3 < w) ? 0xffff0000u : 0u);
+    const u32 mmask01 = ((x_lane >= 0 && x_lane < w) ? 0xffffu : 0u) | ((x_lane + 1 >= 0 && x_lane + 1 < w) ? 0xffff0000u : 0u);
+    const u32 mmask23 = ((x_lane + 2 >= 0 && x_lane + 2 < w) ? 0xffffu : 0u) | ((x_lane + 3 >= 0 && x_lane + 3 < w) ? 0xffff0000u : 0u);
+    const u32 kcmp = (0x7fffu - (u32)lo) * 0x00010001u;
+    const bool vec_store = (w & 3) == 0;
 
-    // ---- loader of one packed gray (or pre-Sobel) word for row r
-    auto load_row = [&](int r, u32 &wa, u32 &wb, u32 &wc) {
+    // ---- general loader of the gray (or pre-Sobel) word of row r: any lane, any row
+    auto load_row = [&](int r) -> u32 {
         const int rr = BLUR ? d_reflect101(r, h) : d_clamp(r, 0, h - 1);
         if (inside && fast_rows) {
             if (BGR) {
                 const u32 *p = (const u32 *)(src + ((size_t)rr * w + x_lane) * 3);
-                wa = __ldg(p); wb = __ldg(p + 1); wc = __ldg(p + 2);
-            } else {
-                wa = __ldg((const u32 *)(src + (size_t)rr * w + x_lane));
+                return gray4(__ldg(p), __ldg(p + 1), __ldg(p + 2));
             }
-        } else {
-            // border lanes / unaligned rows: per-pixel with the border rule, result already gray
-            u32 g = 0;
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                int x = x_lane + k;
-                int xx = BLUR ? d_reflect101(x, w) : d_clamp(x, 0, w - 1);
-                g |= load_px<BGR>(src, rr, xx, w) << (8 * k);
-            }
-            wa = g; wb = 0; wc = 0xffffffffu;  // marker: wa is gray already
+            return __ldg((const u32 *)(src + (size_t)rr * w + x_lane));
         }
-    };
-    auto to_gray = [&](u32 wa, u32 wb, u32 wc) -> u32 {
-        if (BGR) return (inside && fast_rows) ? gray4(wa, wb, wc) : wa;
-        return wa;
+        u32 g = 0;  // border lanes / unaligned rows: per pixel with the border rule
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            int x = x_lane + k;
+            int xx = BLUR ? d_reflect101(x, w) : d_clamp(x, 0, w - 1);
+            g |= load_px<BGR>(src, rr, xx, w) << (8 * k);
+        }
+        return g;
     };
 
-    // ---- pipeline state (packed 16-bit pairs: lo = pixels 0,1; hi = pixels 2,3)
-    u32 a1l = 0, a2l = 0, a3l = 0, a4l = 0, a1h = 0, a2h = 0, a3h = 0, a4h = 0;  // vertical blur (transposed FIR)
-    u32 s1l = 0, s2l = 0, ppl = 0, s1h = 0, s2h = 0, pph = 0;                    // vertical Sobel
-    u32 gxl_p = 0, gxh_p = 0, gyl_p = 0, gyh_p = 0;                              // gradient of the NMS row
-    u32 m_up_l = 0, m_up_h = 0, m_mid_l = 0, m_mid_h = 0;                        // magnitude rows yo-1, yo
-    bool has_mid = false;
+    FrontState S;
+    memset(&S, 0, sizeof(S));
 
-    const int r0 = ys - 2 - LAGB, r1 = ye + 1 + LAGB;  // inclusive input row range
-    u32 na, nb, nc;
-    load_row(r0, na, nb, nc);
-    for (int r = r0; r <= r1; r++) {
-        u32 ca = na, cb = nb, cc = nc;
-        if (r < r1) load_row(r + 1, na, nb, nc);  // prefetch
-        u32 g = to_gray(ca, cb, cc);
+    // One pipeline step: consumes the gray word g of input row r, emits the map word of row r - LAGB - 2.
+    // lean == true drops every border rule (valid for interior strips and rows away from the image
+    // top/bottom and from the segment warm-up), which is the case for most steps.
+    auto step = [&](u32 g, int r, u8 *orow, const bool lean) {
         if (LUT) {
             g = (u32)s_lut[g & 255] | ((u32)s_lut[(g >> 8) & 255] << 8) | ((u32)s_lut[(g >> 16) & 255] << 16) |
                 ((u32)s_lut[g >> 24] << 24);
@@ -167,18 +232,18 @@ __global__ void __launch_bounds__(FR_WARPS * 32) k_front_rows(FrontArgs A)
         if (BLUR) {
             // vertical [1 4 6 4 1] on pairs, transposed form: output row yb = r - 2
             u32 pl = prmt(g, 0, 0x4140), ph = prmt(g, 0, 0x4342);
-            u32 vl = a4l + pl, vh = a4h + ph;
-            a4l = a3l + 4 * pl; a4h = a3h + 4 * ph;
-            a3l = a2l + 6 * pl; a3h = a2h + 6 * ph;
-            a2l = a1l + 4 * pl; a2h = a1h + 4 * ph;
-            a1l = pl; a1h = ph;
+            u32 vl = S.a4l + pl, vh = S.a4h + ph;
+            S.a4l = S.a3l + 4 * pl; S.a4h = S.a3h + 4 * ph;
+            S.a3l = S.a2l + 6 * pl; S.a3h = S.a2h + 6 * ph;
+            S.a2l = S.a1l + 4 * pl; S.a2h = S.a1h + 4 * ph;
+            S.a1l = pl; S.a1h = ph;
             // horizontal on the vertical sums (<= 4080 per half)
             u32 L23 = __shfl_up_sync(~0u, vh, 1), R01 = __shfl_down_sync(~0u, vl, 1);
             u32 Pm10 = prmt(L23, vl, 0x5432), P12 = prmt(vl, vh, 0x5432), P34 = prmt(vh, R01, 0x5432);
             u32 o01 = L23 + vh + 0x00800080u + 4 * (Pm10 + P12) + 6 * vl;
             u32 o23 = vl + R01 + 0x00800080u + 4 * (P12 + P34) + 6 * vh;
             B = prmt(o01, o23, 0x7531);
-            if (need_fix) {
+            if (!lean && need_fix) {
                 u32 nbw = __shfl_sync(~0u, B, fix_src);
                 B = prmt(B, nbw, fix_sel);
             }
@@ -187,98 +252,110 @@ __global__ void __launch_bounds__(FR_WARPS * 32) k_front_rows(FrontArgs A)
         }
         // vertical Sobel on pairs: centre row ysob = yb - 1
         u32 bl = prmt(B, 0, 0x4140), bh = prmt(B, 0, 0x4342);
-        if (BLUR) {
-            if (yb == 0) { s1l = bl; s1h = bh; }                 // B(-1) := B(0)
-            if (yb >= h) { bl = s1l; bh = s1h; }                 // B(H) := B(H-1)
+        if (!lean && BLUR) {
+            if (yb == 0) { S.s1l = bl; S.s1h = bh; }  // B(-1) := B(0)
+            if (yb >= h) { bl = S.s1l; bh = S.s1h; }  // B(H) := B(H-1)
         }
         const int ysob = yb - 1;
-        u32 vsl = s2l + bl, vsh = s2h + bh;                      // B(y-1) + 2 B(y) + B(y+1)
-        u32 vdl = bl + 0x01000100u - ppl, vdh = bh + 0x01000100u - pph;  // B(y+1) - B(y-1) + 256
-        s2l = s1l + 2 * bl; s2h = s1h + 2 * bh;
-        ppl = s1l; pph = s1h;
-        s1l = bl; s1h = bh;
+        u32 vsl = S.s2l + bl, vsh = S.s2h + bh;                              // B(y-1) + 2 B(y) + B(y+1)
+        u32 vdl = bl + 0x01000100u - S.ppl, vdh = bh + 0x01000100u - S.pph;  // B(y+1) - B(y-1) + 256
+        S.s2l = S.s1l + 2 * bl; S.s2h = S.s1h + 2 * bh;
+        S.ppl = S.s1l; S.pph = S.s1h;
+        S.s1l = bl; S.s1h = bh;
         // horizontal Sobel: neighbours' (vs, vd) of pixels -1 and 4
         u32 LN = __shfl_up_sync(~0u, prmt(vsh, vdh, 0x7632), 1);
         u32 RN = __shfl_down_sync(~0u, prmt(vsl, vdl, 0x5410), 1);
         u32 Sm10 = prmt(LN, vsl, 0x5410), S12 = prmt(vsl, vsh, 0x5432), S34 = prmt(vsh, RN, 0x5432);
         u32 Dm10 = prmt(LN, vdl, 0x5432), D12 = prmt(vdl, vdh, 0x5432), D34 = prmt(vdh, RN, 0x7632);
-        u32 gxl = S12 + 0x04000400u - Sm10, gxh = S34 + 0x04000400u - S12;   // gx + 1024
-        u32 gyl = Dm10 + 2 * vdl + D12, gyh = D12 + 2 * vdh + D34;           // gy + 1024
+        u32 gxl = S12 + 0x04000400u - Sm10, gxh = S34 + 0x04000400u - S12;  // gx + 1024
+        u32 gyl = Dm10 + 2 * vdl + D12, gyh = D12 + 2 * vdh + D34;          // gy + 1024
         // |gx| + |gy|
         u32 ml = __vmaxu2(gxl, 0x08000800u - gxl) + __vmaxu2(gyl, 0x08000800u - gyl) - 0x08000800u;
         u32 mh = __vmaxu2(gxh, 0x08000800u - gxh) + __vmaxu2(gyh, 0x08000800u - gyh) - 0x08000800u;
-        const bool row_in = ysob >= 0 && ysob < h;
-        ml = row_in ? (ml & mmask01) : 0u;
-        mh = row_in ? (mh & mmask23) : 0u;
-        const u32 kcmp = (0x7fffu - (u32)lo) * 0x00010001u;
+        if (!lean) {
+            const bool row_in = ysob >= 0 && ysob < h;
+            ml = row_in ? (ml & mmask01) : 0u;
+            mh = row_in ? (mh & mmask23) : 0u;
+        }
         const bool has_new = ((__vmaxu2(ml, mh) + kcmp) & 0x80008000u) != 0;
 
-        // ---- NMS + threshold for row yo = ysob - 1 (magnitudes: up, mid, new)
+        // ---- NMS + threshold for row yo = ysob - 1 (magnitude rows: up, mid, new)
         const int yo = ysob - 1;
-        if (yo >= ys && yo < ye) {
+        if (lean || (yo >= ys && yo < ye)) {
             u32 outw = 0;
-            if (__any_sync(~0u, has_mid)) {
-                // neighbours' magnitudes of pixels -1 (from lane-1, its pixel 3) and 4 (from lane+1, its pixel 0)
-                u32 l_um = __shfl_up_sync(~0u, prmt(m_up_h, m_mid_h, 0x7632), 1);     // lo16 = up(-1), hi16 = mid(-1)
-                u32 l_dn = __shfl_up_sync(~0u, mh >> 16, 1);                           // new(-1)
-                u32 r_um = __shfl_down_sync(~0u, prmt(m_up_l, m_mid_l, 0x5410), 1);   // lo16 = up(4), hi16 = mid(4)
-                u32 r_dn = __shfl_down_sync(~0u, ml & 0xffffu, 1);                     // new(4)
-                if (has_mid) {
-                    int up[6], mid[6], dn[6];
-                    up[0] = l_um & 0xffff; mid[0] = l_um >> 16; dn[0] = l_dn;
-                    up[1] = m_up_l & 0xffff; up[2] = m_up_l >> 16; up[3] = m_up_h & 0xffff; up[4] = m_up_h >> 16;
-                    mid[1] = m_mid_l & 0xffff; mid[2] = m_mid_l >> 16; mid[3] = m_mid_h & 0xffff; mid[4] = m_mid_h >> 16;
-                    dn[1] = ml & 0xffff; dn[2] = ml >> 16; dn[3] = mh & 0xffff; dn[4] = mh >> 16;
-                    up[5] = r_um & 0xffff; mid[5] = r_um >> 16; dn[5] = r_dn;
-                    int gx[4] = {(int)(gxl_p & 0xffff) - 1024, (int)(gxl_p >> 16) - 1024, (int)(gxh_p & 0xffff) - 1024,
-                                 (int)(gxh_p >> 16) - 1024};
-                    int gy[4] = {(int)(gyl_p & 0xffff) - 1024, (int)(gyl_p >> 16) - 1024, (int)(gyh_p & 0xffff) - 1024,
-                                 (int)(gyh_p >> 16) - 1024};
-#pragma unroll
-                    for (int k = 0; k < 4; k++) {
-                        const int mv = mid[k + 1];
-                        if (mv > lo) {
-                            int ax = abs(gx[k]), ay = abs(gy[k]) << 15;
-                            int tg22x = ax * 13573;
-                            bool keep;
-                            if (ay < tg22x) keep = mv > mid[k] && mv >= mid[k + 2];
-                            else {
-                                int tg67x = tg22x + (ax << 16);
-                                if (ay > tg67x) keep = mv > up[k + 1] && mv >= dn[k + 1];
-                                else if ((gx[k] ^ gy[k]) < 0) keep = mv > up[k + 2] && mv > dn[k];
-                                else keep = mv > up[k] && mv > dn[k + 2];
-                            }
-                            if (keep) outw |= (mv > hi ? 255u : 1u) << (8 * k);
-                        }
-                    }
-                }
+            if (__any_sync(~0u, S.has_mid)) {
+                outw = nms_slow(S.mul, S.muh, S.mml, S.mmh, ml, mh, S.gxl, S.gxh, S.gyl, S.gyh, S.has_mid, lo, hi);
                 if (!out_lane) outw = 0;
-                // strong -> front of the queue, weak -> back; pixel index = yo * w + x
-                if (__any_sync(~0u, outw != 0)) {
-#pragma unroll
-                    for (int k = 0; k < 4; k++) {
-                        u32 c = (outw >> (8 * k)) & 255u;
-                        u32 pidx = (u32)(yo * w + x_lane + k);
-                        push_list(c == 255u, pidx, &cnt[LE_C_QTAIL], q, 1, 0, lane);
-                        push_list(c == 1u, pidx, &cnt[LE_C_WEAK], q, -1, npx - 1, lane);
-                    }
-                }
+                if (__any_sync(~0u, outw != 0)) push_out(outw, (u32)(yo * w + x_lane), cnt, q, npx);
             }
             if (out_lane) {
-                u8 *o = map + (size_t)yo * w + x_lane;
-                if ((w & 3) == 0) *(u32 *)o = outw;
+                if (vec_store) *(u32 *)orow = outw;
                 else {
 #pragma unroll
                     for (int k = 0; k < 4; k++)
-                        if (x_lane + k < w) o[k] = (u8)(outw >> (8 * k));
+                        if (x_lane + k < w) orow[k] = (u8)(outw >> (8 * k));
                 }
             }
         }
         // rotate the NMS windows
-        m_up_l = m_mid_l; m_up_h = m_mid_h;
-        m_mid_l = ml; m_mid_h = mh;
-        gxl_p = gxl; gxh_p = gxh; gyl_p = gyl; gyh_p = gyh;
-        has_mid = has_new;
+        S.mul = S.mml; S.muh = S.mmh;
+        S.mml = ml; S.mmh = mh;
+        S.gxl = gxl; S.gxh = gxh; S.gyl = gyl; S.gyh = gyh;
+        S.has_mid = has_new;
+    };
+
+    const int r0 = ys - 2 - LAGB, r1 = ye + 1 + LAGB;  // inclusive input row range
+    // lean steps: interior strip with word-aligned rows; output enabled (r >= ys + LAGB + 2), no top
+    // rule (r >= LAGB + 1) and no bottom rule / all ring rows readable (r <= h - 3)
+    const bool strip_lean = fast_rows && __all_sync(~0u, inside);
+    int ra = max(ys + LAGB + 2, LAGB + 2), rb = min(r1, h - 3);
+    if (!strip_lean || rb < ra) { ra = r1 + 1; rb = r1; }
+    u8 *orow = map + ((long long)(r0 - LAGB - 2) * w + x_lane);  // output row of the step (dereferenced only when valid)
+    int r = r0;
+#pragma unroll 1
+    for (int phase = 0; phase < 2; phase++) {
+        // phase 0: rows before the lean range; phase 1: rows after it (one code instance for both)
+        const int pe = phase == 0 ? min(ra - 1, r1) : r1;
+#pragma unroll 1
+        for (; r <= pe; r++, orow += w) step(load_row(r), r, orow, false);
+        if (phase == 0 && r <= rb) {
+            // steady state: rows stream through the cp.async ring, FR_DEPTH - 1 rows ahead
+            constexpr int WPL = BGR ? 3 : 1;  // words per lane per row
+            const size_t pitch = (size_t)w * WPL;  // bytes per row
+            const u8 *gp = src + ((size_t)r * w + x_lane) * WPL;
+            u32 *ring = &s_ring[wib][0][0];
+            const u32 ring_s = (u32)__cvta_generic_to_shared(ring) + lane * WPL * 4;
+            constexpr u32 ROWB = (BGR ? 96 : 32) * 4;
+            int issue_r = r;  // next row to request
+#pragma unroll
+            for (int d = 0; d < FR_DEPTH - 1; d++) {
+                if (issue_r <= rb) {
+                    u32 sa = ring_s + (u32)(issue_r & (FR_DEPTH - 1)) * ROWB;
+#pragma unroll
+                    for (int k = 0; k < WPL; k++) cp_async4(sa + 4 * k, gp + 4 * k);
+                    gp += pitch;
+                }
+                issue_r++;
+                cp_async_commit();
+            }
+#pragma unroll 1
+            for (; r <= rb; r++, orow += w) {
+                cp_async_wait<FR_DEPTH - 2>();  // the group of row r has landed
+                const u32 *slot = ring + (r & (FR_DEPTH - 1)) * (ROWB / 4) + lane * WPL;
+                u32 ca = slot[0], cb = BGR ? slot[1] : 0, cc = BGR ? slot[2] : 0;
+                // refill the slot consumed in the previous iteration with row r + FR_DEPTH - 1
+                if (issue_r <= rb) {
+                    u32 sa = ring_s + (u32)(issue_r & (FR_DEPTH - 1)) * ROWB;
+#pragma unroll
+                    for (int k = 0; k < WPL; k++) cp_async4(sa + 4 * k, gp + 4 * k);
+                    gp += pitch;
+                }
+                issue_r++;
+                cp_async_commit();
+                step(BGR ? gray4(ca, cb, cc) : ca, r, orow, true);
+            }
+            cp_async_wait<0>();
+        }
     }
 }
 
@@ -288,7 +365,7 @@ static int launch_rows_t(le_ctx *ctx, const u8 *src, u8 *edges, int n, int h, in
     FrontArgs A;
     A.src = src; A.map = edges; A.queue = (u32 *)ctx->queue.p; A.counters = (int *)ctx->counters.p;
     A.lut = (const u8 *)ctx->lut.p;
-    A.h = h; A.w = w; A.lo = min(lo, 4000); A.hi = hi;
+    A.h = h; A.w = w; A.lo = max(0, min(lo, 4000)); A.hi = hi;
     A.nstrips = (w + FR_STRIP - 1) / FR_STRIP;
     // enough warps to fill the machine even for one small frame, long segments for big batches
     long long target_warps = (long long)ctx->sm_count * 32;

@@ -1,19 +1,17 @@
 // le_hough.cu -- standard Hough transform (a5): vote, accumulator write, peaks, ordered output.
 //
 // Design (B200): the accumulator row of one angle only has support on the rho interval the image
-// rectangle projects to (<= image diagonal + 3 bins, although cv2 allocates 2(w+h)+1 bins).  A CTA
+// rectangle projects to (<= image diagonal + a few bins, although cv2 allocates 2(w+h)+1 bins).  A CTA
 // owns one frame and a stripe of A angles (A-2 output rows + 1 halo row each side for the peak
-// test) and keeps that support as packed u16 counters in shared memory (A x span x 2 B).  Voting
+// test) and keeps that support as packed u16 counters in shared memory (A x stride x 2 B).  Voting
 // maps LANES to ANGLES, so a warp-wide shared atomic never has an intra-warp address collision, and
 // a pixel's coordinates are warp-uniform (shuffle broadcast).  Each CTA then streams its rows of
-// the int32 accumulator to HBM exactly once (zeros outside the support) with 128-bit stores and
-// tests peaks straight from shared memory -- the accumulator is never re-read.
+// the int32 accumulator to HBM exactly once with 128-bit stores: zeros outside the support, and
+// inside it one LDS.64 -> four int32 per lane.  The origin of every shared row is shifted by up to
+// 3 bins so that bin 4k of the row lands on a 16-byte boundary of the global row.  Peaks are tested
+// straight from shared memory (packed compare first), so the accumulator is never re-read.
 #include "le_common.cuh"
 #include <vector>
-
-struct HoughGeom {
-    int numangle, numrho, stride;  // stride: u16 bins per smem row (even)
-};
 
 static void hough_dims_host(int h, int w, double rho, double theta, int *numangle, int *numrho)
 {
@@ -36,6 +34,7 @@ extern "C" int le_hough_dims(int h, int w, double rho, double theta, int *numang
 // trig layout in ctx->trig: float cos[na], float sin[na], int rlo[na]
 // kind 0: HoughLinesStandard table (angle accumulates in float32)
 // kind 1: HoughLinesProbabilistic table (cos(double(n)*theta))
+// stride_out: bins per row = support + 4 (room for the alignment shift), multiple of 4
 int le_hough_upload_trig(le_ctx *ctx, int kind, int h, int w, double rho, double theta, int numangle, int *stride_out,
                          cudaStream_t st)
 {
@@ -63,7 +62,7 @@ int le_hough_upload_trig(le_ctx *ctx, int kind, int h, int w, double rho, double
         int rhi = (int)ceil(hi) + 1;
         span = rhi - rlo[n] + 1 > span ? rhi - rlo[n] + 1 : span;
     }
-    *stride_out = (span + 1) & ~1;
+    *stride_out = (span + 4 + 3) & ~3;
     if (ctx->trig_kind == kind && ctx->trig_rho == rho && ctx->trig_theta == theta && ctx->trig_h == h &&
         ctx->trig_w == w)
         return LE_OK;
@@ -85,7 +84,10 @@ int le_hough_upload_trig(le_ctx *ctx, int kind, int h, int w, double rho, double
 
 #define HV_THREADS 512
 
-static __device__ __forceinline__ int hist_get(const u32 *row, int b) { return (row[b >> 1] >> ((b & 1) * 16)) & 0xffff; }
+static __device__ __forceinline__ int hist_get(const u32 *row, int b, int stride)
+{
+    return (b >= 0 && b < stride) ? (int)((row[b >> 1] >> ((b & 1) * 16)) & 0xffff) : 0;
+}
 
 // A = angles per CTA including the two halo rows; 32 % A == 0.
 template <int A>
@@ -106,11 +108,25 @@ k_hough_vote(const u32 *__restrict__ queue, int *__restrict__ counters, const fl
     const int nedge = cnt[LE_C_QTAIL];
     const int n_first = blockIdx.x * (A - 2);  // first output angle of this stripe
     const int *rlo_g = (const int *)(trig + 2 * numangle);
+    const int rowlen = numrho + 2;
+    const int roff = (numrho - 1) / 2 + 1;  // accumulator column of r == 0
+    const size_t asz = (size_t)(numangle + 2) * rowlen;
+    // element index (mod 4) of the frame's accumulator relative to a 16-byte boundary
+    const u32 acc_mis = accum ? (u32)((((size_t)accum >> 2) + (size_t)f * asz) & 3) : 0u;
 
-    for (int i = tid; i < A * hw; i += HV_THREADS) hist[i] = 0;
+    {
+        uint4 *hz = (uint4 *)hist;
+        for (int i = tid; i < A * hw / 4; i += HV_THREADS) hz[i] = make_uint4(0, 0, 0, 0);
+    }
+    // shared row origin: rlo shifted down so that bin 0 sits on a 16-byte boundary of the global row
+    auto row_origin = [&](int n) -> int {
+        int rl = rlo_g[n];
+        u32 e = acc_mis + (u32)(((size_t)(n + 1) * rowlen + roff + rl) & 3);  // misalignment of bin 0
+        return rl - (int)(e & 3);
+    };
     if (tid < A) {
         int n = n_first - 1 + tid;
-        s_rlo[tid] = (n >= 0 && n < numangle) ? rlo_g[n] : 0;
+        s_rlo[tid] = (n >= 0 && n < numangle) ? row_origin(n) : 0;
     }
     // lane -> (angle row a, pixel sub-slot)
     const int a = lane % A, sub = lane / A;
@@ -122,87 +138,88 @@ k_hough_vote(const u32 *__restrict__ queue, int *__restrict__ counters, const fl
     if (row_ok) {
         tcos = trig[n_mine];
         tsin = trig[numangle + n_mine];
-        rlo = rlo_g[n_mine];
+        rlo = row_origin(n_mine);
     }
     u32 *myrow = hist + a * hw;
     __syncthreads();
     for (int base = warp * 32; base < nedge; base += nwarps * 32) {
         int idx = base + lane;
-        int p = idx < nedge ? (int)q[idx] : -1;
-        int py = p / w, px = p - py * w;
+        int p = idx < nedge ? (int)q[idx] : 0;
+        int py = p / w;
+        float fx = (float)(p - py * w), fy = (float)py;
         int cntw = min(32, nedge - base);
 #pragma unroll 4
         for (int j = 0; j < cntw; j += PPW) {
             int src = j + sub;
-            int x = __shfl_sync(~0u, px, src & 31), y = __shfl_sync(~0u, py, src & 31);
+            float x = __shfl_sync(~0u, fx, src & 31), y = __shfl_sync(~0u, fy, src & 31);
             if (row_ok && src < cntw) {
-                float fr = __fadd_rn(__fmul_rn((float)x, tcos), __fmul_rn((float)y, tsin));
-                int b = __float2int_rn(fr) - rlo;
-                atomicAdd(&myrow[b >> 1], (b & 1) ? 0x10000u : 1u);
+                int b = __float2int_rn(__fadd_rn(__fmul_rn(x, tcos), __fmul_rn(y, tsin))) - rlo;
+                atomicAdd(&myrow[b >> 1], 1u << ((b & 1) * 16));
             }
         }
     }
     __syncthreads();
 
     // ---- write the stripe's accumulator rows + peak test
-    const int rowlen = numrho + 2;
-    const int roff = (numrho - 1) / 2 + 1;  // column of r == 0
-    const size_t asz = (size_t)(numangle + 2) * rowlen;
     int32_t *acc_f = accum ? accum + (size_t)f * asz : nullptr;
     u64 *pk = peaks + (size_t)f * peak_cap;
     const int n_last = min(n_first + (A - 2), numangle);  // exclusive
     // rows to write: accumulator rows n+1 for n in [n_first, n_last); plus pad rows 0 and numangle+1
-    const int row_lo = (blockIdx.x == 0) ? -1 : n_first;                    // as angle index n (row n+1)
-    const int row_hi = (n_last == numangle) ? numangle + 1 : n_last;        // exclusive
+    const int row_lo = (blockIdx.x == 0) ? -1 : n_first;              // as angle index n (row n+1)
+    const int row_hi = (n_last == numangle) ? numangle + 1 : n_last;  // exclusive
+    const u32 kcmp = (0x7fffu - (u32)min(max(threshold, 0), 0x7ffe)) * 0x00010001u;
     for (int n = row_lo + warp; n < row_hi; n += nwarps) {
         const int la = n - (n_first - 1);  // local row index
         const bool real = n >= 0 && n < numangle;
         const u32 *row = hist + la * hw;
-        const int rl = real ? s_rlo[la] : 0;
         int32_t *out = acc_f ? acc_f + (size_t)(n + 1) * rowlen : nullptr;
-        // align to 16 B
-        int head = 0;
-        if (out) head = (int)((4 - (((size_t)out >> 2) & 3)) & 3);
-        // columns [0, rowlen): value = hist(col - roff - rl) if real and in [0, stride)
-        for (int c0 = -((4 - head) & 3) + lane * 4; c0 < rowlen; c0 += 128) {
-            // chunk covers columns c0 .. c0+3 (c0 may be negative for the head chunk)
-            int v[4];
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                int c = c0 + k;
-                int b = c - roff - rl;
-                v[k] = (real && c >= 0 && c < rowlen && b >= 0 && b < stride) ? hist_get(row, b) : 0;
+        // support of this row in accumulator columns: [c_lo, c_hi), c_lo is 16-byte aligned when real
+        int c_lo = real ? roff + s_rlo[la] : rowlen, c_hi = real ? c_lo + stride : rowlen;
+        if (out) {
+            // zero fill left of the support, right of it, and the pad rows (scalar head/tail, int4 body)
+            int z0 = 0, z1 = min(max(c_lo, 0), rowlen);
+#pragma unroll 1
+            for (int part = 0; part < 2; part++) {
+                if (z1 > z0) {
+                    int head = (int)((4 - ((((size_t)(out + z0)) >> 2) & 3)) & 3);
+                    int a0 = min(z0 + head, z1), a1 = a0 + ((z1 - a0) & ~3);
+                    for (int c = z0 + lane; c < a0; c += 32) out[c] = 0;
+                    for (int c = a0 + lane * 4; c < a1; c += 128) *(int4 *)(out + c) = make_int4(0, 0, 0, 0);
+                    for (int c = a1 + lane; c < z1; c += 32) out[c] = 0;
+                }
+                z0 = min(max(c_hi, 0), rowlen);
+                z1 = rowlen;
             }
+        }
+        if (!real) continue;
+        // support: 4 bins per lane per step (one LDS.64), aligned int4 store when fully inside the row
+        for (int b0 = lane * 4; b0 < stride; b0 += 128) {
+            const uint2 wv = *(const uint2 *)(row + (b0 >> 1));
+            const int c = c_lo + b0;
             if (out) {
-                if (c0 >= 0 && c0 + 3 < rowlen) *(int4 *)(out + c0) = make_int4(v[0], v[1], v[2], v[3]);
+                if (c >= 0 && c + 3 < rowlen)
+                    *(int4 *)(out + c) = make_int4(wv.x & 0xffff, wv.x >> 16, wv.y & 0xffff, wv.y >> 16);
                 else {
+                    int v[4] = {(int)(wv.x & 0xffff), (int)(wv.x >> 16), (int)(wv.y & 0xffff), (int)(wv.y >> 16)};
 #pragma unroll
                     for (int k = 0; k < 4; k++)
-                        if (c0 + k >= 0 && c0 + k < rowlen) out[c0 + k] = v[k];
+                        if (c + k >= 0 && c + k < rowlen) out[c + k] = v[k];
                 }
             }
-            if (real) {
+            if (((__vmaxu2(wv.x, wv.y) + kcmp) & 0x80008000u) == 0) continue;  // nothing above the threshold
+            int v[4] = {(int)(wv.x & 0xffff), (int)(wv.x >> 16), (int)(wv.y & 0xffff), (int)(wv.y >> 16)};
 #pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    int c = c0 + k;
-                    if (v[k] > threshold && c >= 1 && c <= numrho) {
-                        int b = c - roff - rl;
-                        int left = (b - 1 >= 0) ? hist_get(row, b - 1) : 0;
-                        int right = (b + 1 < stride) ? hist_get(row, b + 1) : 0;
-                        int up = 0, down = 0;
-                        if (n - 1 >= 0) {
-                            int bu = c - roff - s_rlo[la - 1];
-                            if (bu >= 0 && bu < stride) up = hist_get(row - hw, bu);
-                        }
-                        if (n + 1 < numangle) {
-                            int bd = c - roff - s_rlo[la + 1];
-                            if (bd >= 0 && bd < stride) down = hist_get(row + hw, bd);
-                        }
-                        if (v[k] > left && v[k] >= right && v[k] > up && v[k] >= down) {
-                            int pos = atomicAdd(&cnt[LE_C_PEAKS], 1);
-                            u32 idx = (u32)((n + 1) * rowlen + c);
-                            if (pos < peak_cap) pk[pos] = ((u64)(u32)v[k] << 32) | (u64)(0xffffffffu - idx);
-                        }
+            for (int k = 0; k < 4; k++) {
+                const int cc = c + k, b = b0 + k;
+                if (v[k] > threshold && cc >= 1 && cc <= numrho) {
+                    int left = hist_get(row, b - 1, stride), right = hist_get(row, b + 1, stride);
+                    int up = 0, down = 0;
+                    if (n - 1 >= 0) up = hist_get(row - hw, cc - roff - s_rlo[la - 1], stride);
+                    if (n + 1 < numangle) down = hist_get(row + hw, cc - roff - s_rlo[la + 1], stride);
+                    if (v[k] > left && v[k] >= right && v[k] > up && v[k] >= down) {
+                        int pos = atomicAdd(&cnt[LE_C_PEAKS], 1);
+                        u32 idx = (u32)((n + 1) * rowlen + cc);
+                        if (pos < peak_cap) pk[pos] = ((u64)(u32)v[k] << 32) | (u64)(0xffffffffu - idx);
                     }
                 }
             }
@@ -288,6 +305,7 @@ extern "C" int le_hough_lines(le_ctx *ctx, const uint8_t *edges, int n, int h, i
     LE_REQUIRE(ctx, lines && counts && max_lines > 0, "lines/counts must be non-null, max_lines positive");
     LE_REQUIRE(ctx, rho > 0 && theta > 0, "rho and theta must be positive");
     LE_REQUIRE(ctx, (size_t)h * w < ((size_t)1 << 30), "frame too large");
+    LE_REQUIRE(ctx, !accum || (((size_t)accum) & 3) == 0, "accum must be 4-byte aligned");
     cudaSetDevice(ctx->device);
     cudaStream_t st = (cudaStream_t)stream;
     int numangle, numrho, stride;
