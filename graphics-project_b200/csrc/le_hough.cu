@@ -82,7 +82,7 @@ int le_hough_upload_trig(le_ctx *ctx, int kind, int h, int w, double rho, double
     return LE_OK;
 }
 
-#define HV_THREADS 512
+#define HV_THREADS 1024
 
 static __device__ __forceinline__ int hist_get(const u32 *row, int b, int stride)
 {
@@ -98,6 +98,7 @@ k_hough_vote(const u32 *__restrict__ queue, int *__restrict__ counters, const fl
 {
     extern __shared__ __align__(16) u32 hist[];  // [A][stride/2]
     __shared__ int s_rlo[A];
+    __shared__ float2 s_stage[HV_THREADS / 32][32];
     const int f = blockIdx.y;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nwarps = HV_THREADS / 32;
@@ -140,21 +141,37 @@ k_hough_vote(const u32 *__restrict__ queue, int *__restrict__ counters, const fl
         tsin = trig[numangle + n_mine];
         rlo = row_origin(n_mine);
     }
-    u32 *myrow = hist + a * hw;
+    // 32-bit shared address of this lane's row; lanes of rows outside [0, numangle) add 0 (branch-free)
+    const u32 row_sa = (u32)__cvta_generic_to_shared(hist + a * hw);
+    const u32 one = row_ok ? 1u : 0u;
+    float2 *stage = s_stage[warp];
     __syncthreads();
     for (int base = warp * 32; base < nedge; base += nwarps * 32) {
+        // each lane converts one queue entry to float (x, y) and stages it; the warp then votes the
+        // 32 pixels with one broadcast LDS.64 per pixel (per PPW pixels when A < 32)
         int idx = base + lane;
         int p = idx < nedge ? (int)q[idx] : 0;
         int py = p / w;
-        float fx = (float)(p - py * w), fy = (float)py;
-        int cntw = min(32, nedge - base);
-#pragma unroll 4
-        for (int j = 0; j < cntw; j += PPW) {
-            int src = j + sub;
-            float x = __shfl_sync(~0u, fx, src & 31), y = __shfl_sync(~0u, fy, src & 31);
-            if (row_ok && src < cntw) {
-                int b = __float2int_rn(__fadd_rn(__fmul_rn(x, tcos), __fmul_rn(y, tsin))) - rlo;
-                atomicAdd(&myrow[b >> 1], 1u << ((b & 1) * 16));
+        __syncwarp();
+        stage[lane] = make_float2((float)(p - py * w), (float)py);
+        __syncwarp();
+        const int cntw = min(32, nedge - base);
+        if (cntw == 32) {
+#pragma unroll 8
+            for (int j = 0; j < 32; j += PPW) {
+                float2 xy = stage[j + sub];
+                int b = __float2int_rn(__fadd_rn(__fmul_rn(xy.x, tcos), __fmul_rn(xy.y, tsin))) - rlo;
+                u32 sa = row_sa + (((u32)b << 1) & ~3u);
+                u32 val = one << (((u32)b & 1u) << 4);
+                asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(sa), "r"(val) : "memory");
+            }
+        } else {
+            for (int j = 0; j < cntw; j += PPW) {
+                float2 xy = stage[(j + sub) & 31];
+                int b = __float2int_rn(__fadd_rn(__fmul_rn(xy.x, tcos), __fmul_rn(xy.y, tsin))) - rlo;
+                u32 sa = row_sa + (((u32)b << 1) & ~3u);
+                u32 val = (j + sub < cntw ? one : 0u) << (((u32)b & 1u) << 4);
+                asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(sa), "r"(val) : "memory");
             }
         }
     }
@@ -324,7 +341,7 @@ extern "C" int le_hough_lines(le_ctx *ctx, const uint8_t *edges, int n, int h, i
     if (rc) return rc;
     k_zero_peaks<<<(n + 255) / 256, 256, 0, st>>>((int *)ctx->counters.p, n);
     LE_LAUNCH_CHECK(ctx);
-    size_t budget = (size_t)ctx->smem_optin - 1024;
+    size_t budget = (size_t)ctx->smem_optin - 1024 - sizeof(float2) * HV_THREADS;
     if ((size_t)32 * stride * 2 <= budget) rc = launch_vote<32>(ctx, n, h, w, numangle, numrho, stride, threshold, accum, peak_cap, st);
     else if ((size_t)16 * stride * 2 <= budget) rc = launch_vote<16>(ctx, n, h, w, numangle, numrho, stride, threshold, accum, peak_cap, st);
     else if ((size_t)8 * stride * 2 <= budget) rc = launch_vote<8>(ctx, n, h, w, numangle, numrho, stride, threshold, accum, peak_cap, st);
