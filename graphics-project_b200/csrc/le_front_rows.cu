@@ -19,8 +19,9 @@
 #define FR_STRIP 120
 #define FR_WARPS 4
 #define FR_DEPTH 8  // rows in the cp.async ring (prefetch distance FR_DEPTH - 1)
+#define FR_FLAT 9  // identical constant rows after which the pipeline state is at its fixed point
 #ifndef FR_MINBLK
-#define FR_MINBLK 8
+#define FR_MINBLK 6
 #endif
 #ifndef FR_UNROLL
 #define FR_UNROLL 2
@@ -196,6 +197,20 @@ __global__ void __launch_bounds__(FR_WARPS * 32, FR_MINBLK) k_front_rows(FrontAr
     const u32 kcmp = (0x7fffu - (u32)lo) * 0x00010001u;
     const bool vec_store = (w & 3) == 0;
 
+    // lean path at the left/right image border: out-of-image words are rebuilt from in-image lanes
+    // (REFLECT_101 before a blur, replicate otherwise); their own loads use a clamped address
+    const bool xborder = __any_sync(~0u, !inside);
+    int gsx = lane, gsy = lane;
+    u32 gsel = 0x3210;
+    if (x_lane < 0) { gsx = lane + 1; gsy = lane + 2; gsel = BLUR ? 0x1234 : 0x0000; }
+    else if (x_lane >= w) {
+        int j = (x_lane - w) >> 2;
+        if (BLUR) { gsx = lane - 2 - 2 * j; gsy = lane - 1 - 2 * j; gsel = 0x3456; }
+        else { gsx = gsy = lane - 1 - j; gsel = 0x7777; }
+    }
+    gsx = min(max(gsx, 0), 31); gsy = min(max(gsy, 0), 31);
+    const int x_ld = min(max(x_lane, 0), max(w - 4, 0));  // load position (always inside the row)
+
     // ---- general loader of the gray (or pre-Sobel) word of row r: any lane, any row
     auto load_row = [&](int r) -> u32 {
         const int rr = BLUR ? d_reflect101(r, h) : d_clamp(r, 0, h - 1);
@@ -222,7 +237,7 @@ __global__ void __launch_bounds__(FR_WARPS * 32, FR_MINBLK) k_front_rows(FrontAr
     // One pipeline step: consumes the gray word g of input row r, emits the map word of row r - LAGB - 2.
     // lean == true drops every border rule (valid for interior strips and rows away from the image
     // top/bottom and from the segment warm-up), which is the case for most steps.
-    auto step = [&](u32 g, int r, u8 *orow, const bool lean) {
+    auto step = [&](u32 g, int r, u8 *orow, const bool lean, const bool emit) {
         if (LUT) {
             g = (u32)s_lut[g & 255] | ((u32)s_lut[(g >> 8) & 255] << 8) | ((u32)s_lut[(g >> 16) & 255] << 16) |
                 ((u32)s_lut[g >> 24] << 24);
@@ -243,7 +258,7 @@ __global__ void __launch_bounds__(FR_WARPS * 32, FR_MINBLK) k_front_rows(FrontAr
             u32 o01 = L23 + vh + 0x00800080u + 4 * (Pm10 + P12) + 6 * vl;
             u32 o23 = vl + R01 + 0x00800080u + 4 * (P12 + P34) + 6 * vh;
             B = prmt(o01, o23, 0x7531);
-            if (!lean && need_fix) {
+            if (need_fix) {  // warp-uniform: only strips that touch the left/right image border
                 u32 nbw = __shfl_sync(~0u, B, fix_src);
                 B = prmt(B, nbw, fix_sel);
             }
@@ -274,14 +289,15 @@ __global__ void __launch_bounds__(FR_WARPS * 32, FR_MINBLK) k_front_rows(FrontAr
         u32 mh = __vmaxu2(gxh, 0x08000800u - gxh) + __vmaxu2(gyh, 0x08000800u - gyh) - 0x08000800u;
         if (!lean) {
             const bool row_in = ysob >= 0 && ysob < h;
-            ml = row_in ? (ml & mmask01) : 0u;
-            mh = row_in ? (mh & mmask23) : 0u;
+            ml = row_in ? ml : 0u;
+            mh = row_in ? mh : 0u;
         }
+        if (xborder) { ml &= mmask01; mh &= mmask23; }  // warp-uniform
         const bool has_new = ((__vmaxu2(ml, mh) + kcmp) & 0x80008000u) != 0;
 
         // ---- NMS + threshold for row yo = ysob - 1 (magnitude rows: up, mid, new)
         const int yo = ysob - 1;
-        if (lean || (yo >= ys && yo < ye)) {
+        if (emit) {
             u32 outw = 0;
             if (__any_sync(~0u, S.has_mid)) {
                 outw = nms_slow(S.mul, S.muh, S.mml, S.mmh, ml, mh, S.gxl, S.gxh, S.gyl, S.gyh, S.has_mid, lo, hi);
@@ -307,9 +323,10 @@ __global__ void __launch_bounds__(FR_WARPS * 32, FR_MINBLK) k_front_rows(FrontAr
     const int r0 = ys - 2 - LAGB, r1 = ye + 1 + LAGB;  // inclusive input row range
     // lean steps: interior strip with word-aligned rows; output enabled (r >= ys + LAGB + 2), no top
     // rule (r >= LAGB + 1) and no bottom rule / all ring rows readable (r <= h - 3)
-    const bool strip_lean = fast_rows && __all_sync(~0u, inside);
-    int ra = max(ys + LAGB + 2, LAGB + 2), rb = min(r1, h - 3);
+    const bool strip_lean = fast_rows && w >= 16;
+    int ra = max(r0, LAGB + 1), rb = min(r1, h - 3);
     if (!strip_lean || rb < ra) { ra = r1 + 1; rb = r1; }
+    auto emit_row = [&](int rr) { int yo = rr - LAGB - 2; return yo >= ys && yo < ye; };
     u8 *orow = map + ((long long)(r0 - LAGB - 2) * w + x_lane);  // output row of the step (dereferenced only when valid)
     int r = r0;
 #pragma unroll 1
@@ -317,12 +334,12 @@ __global__ void __launch_bounds__(FR_WARPS * 32, FR_MINBLK) k_front_rows(FrontAr
         // phase 0: rows before the lean range; phase 1: rows after it (one code instance for both)
         const int pe = phase == 0 ? min(ra - 1, r1) : r1;
 #pragma unroll 1
-        for (; r <= pe; r++, orow += w) step(load_row(r), r, orow, false);
+        for (; r <= pe; r++, orow += w) step(load_row(r), r, orow, false, emit_row(r));
         if (phase == 0 && r <= rb) {
             // steady state: rows stream through the cp.async ring, FR_DEPTH - 1 rows ahead
             constexpr int WPL = BGR ? 3 : 1;  // words per lane per row
             const size_t pitch = (size_t)w * WPL;  // bytes per row
-            const u8 *gp = src + ((size_t)r * w + x_lane) * WPL;
+            const u8 *gp = src + ((size_t)r * w + x_ld) * WPL;
             u32 *ring = &s_ring[wib][0][0];
             const u32 ring_s = (u32)__cvta_generic_to_shared(ring) + lane * WPL * 4;
             constexpr u32 ROWB = (BGR ? 96 : 32) * 4;
@@ -338,12 +355,12 @@ __global__ void __launch_bounds__(FR_WARPS * 32, FR_MINBLK) k_front_rows(FrontAr
                 issue_r++;
                 cp_async_commit();
             }
-#pragma unroll 1
-            for (; r <= rb; r++, orow += w) {
-                cp_async_wait<FR_DEPTH - 2>();  // the group of row r has landed
-                const u32 *slot = ring + (r & (FR_DEPTH - 1)) * (ROWB / 4) + lane * WPL;
-                u32 ca = slot[0], cb = BGR ? slot[1] : 0, cc = BGR ? slot[2] : 0;
-                // refill the slot consumed in the previous iteration with row r + FR_DEPTH - 1
+            // Flat-row skip: once FR_FLAT consecutive rows of this strip were one constant, every
+            // pipeline register sits at its fixed point (partial sums of a constant, zero magnitudes),
+            // so a further identical row leaves the state untouched and its output row is zero.
+            u32 pa = 0, pb = 0, pc = 0, gprev = 0;
+            int flat = 0;
+            auto refill = [&]() {  // request row issue_r into the slot consumed one iteration ago
                 if (issue_r <= rb) {
                     u32 sa = ring_s + (u32)(issue_r & (FR_DEPTH - 1)) * ROWB;
 #pragma unroll
@@ -352,7 +369,42 @@ __global__ void __launch_bounds__(FR_WARPS * 32, FR_MINBLK) k_front_rows(FrontAr
                 }
                 issue_r++;
                 cp_async_commit();
-                step(BGR ? gray4(ca, cb, cc) : ca, r, orow, true);
+            };
+#pragma unroll 1
+            while (r <= rb) {
+                cp_async_wait<FR_DEPTH - 2>();  // the group of row r has landed
+                const u32 *slot = ring + (r & (FR_DEPTH - 1)) * (ROWB / 4) + lane * WPL;
+                u32 ca = slot[0], cb = BGR ? slot[1] : 0, cc = BGR ? slot[2] : 0;
+                if (flat >= FR_FLAT) {
+                    // tight loop over rows identical to the previous one: nothing but load, compare, store 0
+#pragma unroll 1
+                    while (__all_sync(~0u, ((ca ^ pa) | (cb ^ pb) | (cc ^ pc)) == 0)) {
+                        refill();
+                        if (out_lane && emit_row(r)) *(u32 *)orow = 0u;  // lean implies w % 4 == 0
+                        r++;
+                        orow += w;
+                        if (r > rb) break;
+                        cp_async_wait<FR_DEPTH - 2>();
+                        slot = ring + (r & (FR_DEPTH - 1)) * (ROWB / 4) + lane * WPL;
+                        ca = slot[0]; cb = BGR ? slot[1] : 0; cc = BGR ? slot[2] : 0;
+                    }
+                    if (r > rb) break;
+                }
+                refill();
+                pa = ca; pb = cb; pc = cc;
+                u32 g = BGR ? gray4(ca, cb, cc) : ca;
+                if (xborder) {  // warp-uniform
+                    u32 gx_ = __shfl_sync(~0u, g, gsx), gy_ = __shfl_sync(~0u, g, gsy);
+                    g = prmt(gx_, gy_, gsel);
+                }
+                int all_eq;
+                __match_all_sync(~0u, g, &all_eq);
+                const bool row_const = all_eq && g == prmt(g, 0, 0x0000);  // warp-uniform
+                flat = row_const ? ((flat > 0 && g == gprev) ? flat + 1 : 1) : 0;
+                gprev = g;
+                step(g, r, orow, true, emit_row(r));
+                r++;
+                orow += w;
             }
             cp_async_wait<0>();
         }
@@ -369,7 +421,7 @@ static int launch_rows_t(le_ctx *ctx, const u8 *src, u8 *edges, int n, int h, in
     A.nstrips = (w + FR_STRIP - 1) / FR_STRIP;
     // enough warps to fill the machine even for one small frame, long segments for big batches
     long long target_warps = (long long)ctx->sm_count * 32;
-    int rows = 72;
+    int rows = 120;
     while (rows > 8 && (long long)n * A.nstrips * ((h + rows - 1) / rows) < target_warps) rows /= 2;
     A.rows_per_seg = rows;
     A.nsegs = (h + rows - 1) / rows;

@@ -109,3 +109,32 @@ def test_shim_rejects_off_path_parameters_without_gpu():
         cv.createLineSegmentDetector(2)
     assert cv.COLOR_BGR2GRAY == 6 and cv.NORM_MINMAX == 32
     assert callable(cv.imread)  # non-hot-path attributes are forwarded to the real cv2
+
+
+def test_shim_install_lets_reference_import_unchanged():
+    """INTEGRATION.md route A: with the shim at sys.modules['cv2'] the reference's own modules import and
+    bind the GPU entry points (skipped where the reference checkout is absent, e.g. on the GPU box)."""
+    import subprocess
+    import sys
+    if not os.path.isdir("/root/reference"):
+        pytest.skip("reference checkout not present")
+    code = r'''
+import sys, types, os
+sys.dont_write_bytecode = True
+sys.path.insert(0, %r)
+import graphics_project_b200 as gp
+shim = gp.cv_shim.install()
+for name in ("moderngl", "matplotlib", "matplotlib.pyplot", "mpl_toolkits", "mpl_toolkits.mplot3d"):
+    sys.modules.setdefault(name, types.ModuleType(name))
+sys.modules["moderngl"].Framebuffer = object; sys.modules["moderngl"].Context = object
+sys.modules["mpl_toolkits.mplot3d"].Axes3D = object
+sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
+os.chdir("/root/reference"); sys.path.insert(0, "/root/reference")
+import opencv, opencv_fit_color, opencv_renewed
+assert opencv.cv is shim and opencv_fit_color.cv is shim
+assert opencv.cv.Canny is shim.Canny and opencv.cv.HoughLinesP is shim.HoughLinesP
+assert opencv.cv.imread is not None and opencv.cv.COLOR_BGR2GRAY == 6
+print("ok")
+''' % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stderr[-2000:]
