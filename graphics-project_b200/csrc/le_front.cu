@@ -322,6 +322,49 @@ __global__ void __launch_bounds__(1024) k_hysteresis(u8 *__restrict__ map, u32 *
     int head = 0, tail = cnt[LE_C_QTAIL];
     const int nweak = cnt[LE_C_WEAK];
     const long long cap = (long long)npx - nweak;  // front may use [0, cap)
+    if (nweak == 0) return;  // nothing to promote, nothing to clear (block-uniform)
+    if (nweak <= 4096 && tail + nweak <= cap) {
+        // Few weak candidates (the usual case when hi is low): sweep the WEAK list instead of flooding
+        // from every strong pixel.  A weak pixel with a 255 neighbour is promoted; repeat to a fixpoint.
+        __shared__ int s_changed, s_t2;
+        if (threadIdx.x == 0) s_t2 = tail;
+        for (;;) {
+            __syncthreads();
+            if (threadIdx.x == 0) s_changed = 0;
+            __syncthreads();
+            for (int i = threadIdx.x; i < nweak; i += blockDim.x) {
+                u32 p = q[npx - 1 - i];
+                if (__ldcg(m + p) != 1) continue;
+                int y = (int)(p / (u32)w), x = (int)(p - (u32)y * w);
+                // all 8 neighbour reads are issued together (one L2 round trip, no early exit)
+                int nb[8];
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    const int dy = (k < 3) ? -1 : (k < 5 ? 0 : 1);
+                    const int dx = (k < 3) ? k - 1 : (k == 3 ? -1 : (k == 4 ? 1 : k - 6));
+                    int yy = y + dy, xx = x + dx;
+                    bool in = yy >= 0 && yy < h && xx >= 0 && xx < w;
+                    nb[k] = in ? (int)__ldcg(m + (size_t)(in ? yy : y) * w + (in ? xx : x)) : 0;
+                }
+                bool hit = false;
+#pragma unroll
+                for (int k = 0; k < 8; k++) hit |= nb[k] == 255;
+                if (hit) {
+                    __stcg(m + p, (u8)255);  // single owner: this pixel appears once in the weak list
+                    q[atomicAdd(&s_t2, 1)] = p;
+                    s_changed = 1;
+                }
+            }
+            __syncthreads();
+            if (!s_changed) break;
+        }
+        for (int i = threadIdx.x; i < nweak; i += blockDim.x) {
+            u32 p = q[npx - 1 - i];
+            if (__ldcg(m + p) == 1) __stcg(m + p, (u8)0);
+        }
+        if (threadIdx.x == 0) cnt[LE_C_QTAIL] = s_t2;
+        return;
+    }
     if (threadIdx.x == 0) { s_tail = tail; s_over = 0; }
     __syncthreads();
     while (head < tail) {

@@ -1,0 +1,58 @@
+"""Throughput of the other hot-path rows (HoughLinesP, LSD, VP) on synthetic batches; prints JSON lines."""
+import json, sys, time
+sys.path.insert(0, "/root/repo")
+import numpy as np, torch
+import graphics_project_b200 as gp
+
+def timeit(fn, reps=3):
+    fn(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps): fn()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+eng = gp.Engine(0)
+def frames(n, h, w, kind, uniq=16):
+    u = gp.synth.make_batch(min(uniq, n), h, w, kind)
+    return torch.from_numpy(np.stack([u[i % len(u)] for i in range(n)])).cuda()
+
+out = []
+for (n, h, w, kind) in ((256, 1080, 1920, "cubes"), (64, 2160, 3840, "cubes")):
+    t = frames(n, h, w, kind)
+    edges = eng.front_canny(t, 5, 150)
+    eng.timing(True); eng.timing_read()
+    ms = timeit(lambda: (eng.front_canny(t, 5, 150, out=edges), eng.hough_lines_p(edges, 1, np.pi/180, 30, 50, 10)))
+    kt = {k: round(v[0]/v[1], 3) for k, v in eng.timing_read().items()}; eng.timing(False)
+    segs, counts = eng.hough_lines_p(edges, 1, np.pi/180, 30, 50, 10)
+    out.append({"chain": "prob: Canny(5,150)+HoughLinesP(30,50,10)", "n": n, "h": h, "w": w, "ms": round(ms, 3), "fps": round(n / ms * 1e3), "kernels_ms": kt, "segs_mean": float(counts.float().mean())})
+    print(json.dumps(out[-1]), flush=True)
+    del t, edges
+for (n, h, w, kind) in ((128, 1080, 1920, "voxel"), (128, 1080, 1920, "cave")):
+    t = frames(n, h, w, kind)
+    gray = eng.bgr2gray(t); del t
+    eng.timing(True); eng.timing_read()
+    ms = timeit(lambda: eng.lsd(gray), reps=2)
+    kt = {k: round(v[0]/v[1], 3) for k, v in eng.timing_read().items()}; eng.timing(False)
+    segs, _, _, counts = eng.lsd(gray)
+    out.append({"chain": "lsd(refine 0, scale .8)", "kind": kind, "n": n, "h": h, "w": w, "ms": round(ms, 3), "fps": round(n / ms * 1e3), "kernels_ms": kt, "segs_mean": float(counts.float().mean())})
+    print(json.dumps(out[-1]), flush=True)
+    del gray
+# VP: regress_lines on LSD segments of one frame
+img = gp.synth.make_frame(1, 400, 600, "voxel")
+pairs = gp.detectors.lsd(img)
+lines = gp.vp.edges_to_polar_lines(pairs)
+t0 = time.perf_counter(); (phi, theta), loss = gp.vp.regress_lines(lines, 1000, 500, np.deg2rad(15), verbose=False); dt = time.perf_counter() - t0
+print(json.dumps({"chain": "regress_lines(1000,500,15deg)", "lines": len(lines), "seconds": round(dt, 4), "loss": loss}))
+# CPU side for comparison (cv2, single frame, single thread)
+import cv2 as cv
+cv.setNumThreads(1)
+f = gp.synth.make_frame(0, 1080, 1920, "cubes"); g = cv.cvtColor(f, cv.COLOR_BGR2GRAY)
+t0 = time.perf_counter()
+for _ in range(5): e = cv.Canny(cv.cvtColor(f, cv.COLOR_BGR2GRAY), 5, 150); cv.HoughLinesP(e, 1, np.pi/180, 30, minLineLength=50, maxLineGap=10)
+print(json.dumps({"cv2_1thread_prob_1080p_ms": round((time.perf_counter() - t0) / 5 * 1e3, 2)}))
+f = gp.synth.make_frame(0, 1080, 1920, "voxel"); g = cv.cvtColor(f, cv.COLOR_BGR2GRAY)
+d = cv.createLineSegmentDetector(0, scale=.8, sigma_scale=.6, quant=2.0, ang_th=22.5, log_eps=0, density_th=.7, n_bins=1024)
+t0 = time.perf_counter()
+for _ in range(3): d.detect(g)
+print(json.dumps({"cv2_1thread_lsd_1080p_voxel_ms": round((time.perf_counter() - t0) / 3 * 1e3, 2)}))
