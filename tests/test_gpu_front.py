@@ -104,3 +104,46 @@ def test_batch_independence_and_idempotence(engine):
             assert torch.equal(e1[j], single[0])
     assert set(torch.unique(e1).tolist()) <= {0, 255}
     engine.check()
+
+
+@pytest.mark.parametrize("shape", [(40, 16), (9, 20), (30, 120), (30, 124), (50, 128), (25, 240), (25, 244), (64, 600),
+                                   (300, 132), (12, 1920)])
+def test_lean_path_borders_and_flat_skip(engine, shape):
+    """Widths that are multiples of 4 take the streaming (lean) path, including strips that touch the
+    left/right border; big constant areas with sparse structure exercise the flat-row skip and its
+    re-entry.  Both BGR and gray inputs, with and without blur."""
+    h, w = shape
+    rng = np.random.default_rng(h * 1000 + w)
+    imgs = np.full((3, h, w, 3), 200, np.uint8)
+    imgs[0] = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)           # noise: never flat
+    imgs[1, h // 3: h // 3 + max(1, h // 5), w // 4: w // 2] = (30, 60, 90)   # a box on a flat background
+    imgs[1, :, -1] = 0                                                     # structure at the right border
+    imgs[2, ::max(2, h // 3), :] = 10                                      # a few horizontal lines, flat between
+    imgs[2, :, 0] = 255                                                    # structure at the left border
+    t = dev(imgs)
+    g = np.stack([R.bgr2gray(i) for i in imgs])
+    for lo, hi, blur in ((5, 10, True), (5, 150, False), (30, 50, True)):
+        e = engine.front_canny(t, lo, hi, blur=blur).cpu().numpy()
+        eg = engine.front_canny(dev(g), lo, hi, blur=blur).cpu().numpy()
+        for i in range(3):
+            src = R.gauss5(g[i]) if blur else g[i]
+            ref = R.canny(src, lo, hi)
+            assert np.array_equal(e[i], ref), (shape, lo, hi, blur, i, "bgr")
+            assert np.array_equal(eg[i], ref), (shape, lo, hi, blur, i, "gray")
+    engine.check()
+
+
+def test_many_weak_candidates_use_bfs_path(engine):
+    """Low/high thresholds far apart on noisy gradients: thousands of weak candidates per frame, so the
+    hysteresis kernel takes the flood-from-strong path instead of the weak-list sweep."""
+    rng = np.random.default_rng(5)
+    h, w = 240, 320
+    base = np.cumsum(rng.integers(-1, 2, (2, h, w)), axis=2) + np.cumsum(rng.integers(-1, 2, (2, h, w)), axis=1)
+    g = np.clip(base + 128, 0, 255).astype(np.uint8)
+    for lo, hi in ((2, 60), (2, 90)):
+        e = engine.canny(dev(g), lo, hi).cpu().numpy()
+        for i in range(2):
+            ref, nms = R.canny(g[i], lo, hi, return_nms=True)
+            assert (nms == 1).sum() > 4096
+            assert np.array_equal(e[i], ref)
+    engine.check()
