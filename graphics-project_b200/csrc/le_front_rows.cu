@@ -17,11 +17,11 @@
 #include "le_common.cuh"
 
 #define FR_STRIP 120
-#define FR_WARPS 4
+#define FR_WARPS 1
 #define FR_DEPTH 8  // rows in the cp.async ring (prefetch distance FR_DEPTH - 1)
 #define FR_FLAT 9  // identical constant rows after which the pipeline state is at its fixed point
 #ifndef FR_MINBLK
-#define FR_MINBLK 6
+#define FR_MINBLK 24
 #endif
 #ifndef FR_UNROLL
 #define FR_UNROLL 2

@@ -12,6 +12,7 @@
 // straight from shared memory (packed compare first), so the accumulator is never re-read.
 #include "le_common.cuh"
 #include <vector>
+#include <stdlib.h>
 
 static void hough_dims_host(int h, int w, double rho, double theta, int *numangle, int *numrho)
 {
@@ -342,10 +343,18 @@ extern "C" int le_hough_lines(le_ctx *ctx, const uint8_t *edges, int n, int h, i
     k_zero_peaks<<<(n + 255) / 256, 256, 0, st>>>((int *)ctx->counters.p, n);
     LE_LAUNCH_CHECK(ctx);
     size_t budget = (size_t)ctx->smem_optin - 1024 - sizeof(float2) * HV_THREADS;
-    if ((size_t)32 * stride * 2 <= budget) rc = launch_vote<32>(ctx, n, h, w, numangle, numrho, stride, threshold, accum, peak_cap, st);
-    else if ((size_t)16 * stride * 2 <= budget) rc = launch_vote<16>(ctx, n, h, w, numangle, numrho, stride, threshold, accum, peak_cap, st);
-    else if ((size_t)8 * stride * 2 <= budget) rc = launch_vote<8>(ctx, n, h, w, numangle, numrho, stride, threshold, accum, peak_cap, st);
-    else if ((size_t)4 * stride * 2 <= budget) rc = launch_vote<4>(ctx, n, h, w, numangle, numrho, stride, threshold, accum, peak_cap, st);
+    // angles per CTA: the largest stripe whose counters leave room for two resident CTAs per SM (their
+    // zero / vote / write phases then overlap); fall back to whatever fits one CTA
+    size_t two = budget / 2 - 4096;
+    int A = 0;
+    for (int cand = 32; cand >= 8 && !A; cand >>= 1)
+        if ((size_t)cand * stride * 2 <= two) A = cand;
+    for (int cand = 32; cand >= 4 && !A; cand >>= 1)
+        if ((size_t)cand * stride * 2 <= budget) A = cand;
+    if (A == 32) rc = launch_vote<32>(ctx, n, h, w, numangle, numrho, stride, threshold, accum, peak_cap, st);
+    else if (A == 16) rc = launch_vote<16>(ctx, n, h, w, numangle, numrho, stride, threshold, accum, peak_cap, st);
+    else if (A == 8) rc = launch_vote<8>(ctx, n, h, w, numangle, numrho, stride, threshold, accum, peak_cap, st);
+    else if (A == 4) rc = launch_vote<4>(ctx, n, h, w, numangle, numrho, stride, threshold, accum, peak_cap, st);
     else return le_fail(ctx, LE_ERR_UNSUPPORTED, "image too large for the shared-memory Hough stripes (stride %d)", stride);
     if (rc) return rc;
     LE_T0(ctx, LE_K_SORT, st);
