@@ -9,7 +9,11 @@
 // The accumulator keeps only the rho support of each angle (s16 [numangle][stride], ~0.8 MB at
 // 1080p instead of cv2's 4.3 MB int32) so the working set of all resident frames stays in L2.
 #include "le_common.cuh"
+#include <stdlib.h>
 
+int le_ppht_fast_launch(le_ctx *ctx, int n, int h, int w, int numangle, int stride, int threshold, int min_len,
+                        int max_gap, int32_t *segs, int32_t *counts, int max_segs, int32_t *trace, int trace_cap,
+                        cudaStream_t st);
 int le_hough_upload_trig(le_ctx *ctx, int kind, int h, int w, double rho, double theta, int numangle, int *stride_out,
                          cudaStream_t st);
 
@@ -132,14 +136,18 @@ k_ppht(u8 *__restrict__ mask, u32 *__restrict__ nz_g, short *__restrict__ accum,
     }
     u64 rng = ~0ULL;
     int par = 0;
+    long long dbg_t[4] = {0, 0, 0, 0}, dbg_picks = 0, dbg_votes = 0;  // only touched when tracing
     __syncthreads();
     const int shift = 16;
     for (;;) {
         // thread 0 is the producer: it replays cv::RNG, maintains the swap-remove list and skips
         // picks whose pixel was already consumed (no barrier needed for those)
+        long long t_a = 0;
+        if (trace && tid == 0) t_a = clock64();
         if (tid == 0) {
             int pick = -1;
             while (count > 0) {
+                if (trace) dbg_picks++;
                 int idx = (int)(rng_next(rng) % (u32)count);
                 u32 pt = nz[idx];
                 nz[idx] = nz[count - 1];
@@ -149,6 +157,7 @@ k_ppht(u8 *__restrict__ mask, u32 *__restrict__ nz_g, short *__restrict__ accum,
             S.pick[par] = pick;
         }
         __syncthreads();
+        if (trace && tid == 0) { long long t = clock64(); dbg_t[0] += t - t_a; t_a = t; }
         const int pk = S.pick[par];
         par ^= 1;
         if (pk < 0) break;
@@ -184,6 +193,7 @@ k_ppht(u8 *__restrict__ mask, u32 *__restrict__ nz_g, short *__restrict__ accum,
         for (int k = 1; k < PP_THREADS / 32; k++) best = S.red[k] > best ? S.red[k] : best;
         const int max_val = (int)(best >> 32) - 0x8000;  // biased so that negative cells order correctly
         const int max_n = 0x7fffffff - (int)(u32)best;
+        if (trace && tid == 0) { long long t = clock64(); dbg_t[1] += t - t_a; t_a = t; dbg_votes++; }
         if (max_val < threshold) continue;  // uniform (needs no barrier: S.red is rewritten only after the next sync)
         // ---- walk set-up (all threads, identical)
         const float a = -trig[numangle + max_n], b = trig[max_n];
@@ -236,6 +246,7 @@ k_ppht(u8 *__restrict__ mask, u32 *__restrict__ nz_g, short *__restrict__ accum,
             }
         }
         __syncthreads();
+        if (trace && tid == 0) { long long t = clock64(); dbg_t[2] += t - t_a; t_a = t; }
         const int e0x = S.end_xy[0][0], e0y = S.end_xy[0][1], e1x = S.end_xy[1][0], e1y = S.end_xy[1][1];
         const bool good = abs(e1x - e0x) >= line_length || abs(e1y - e0y) >= line_length;
         if (trace && f == 0 && tid == 0) {
@@ -278,6 +289,7 @@ k_ppht(u8 *__restrict__ mask, u32 *__restrict__ nz_g, short *__restrict__ accum,
                 }
             }
         }
+        if (trace && tid == 0) { long long t = clock64(); dbg_t[3] += t - t_a; t_a = t; }
         if (good && tid == 0) {
             int pos = S.nlines++;
             if (pos < max_segs) {
@@ -288,6 +300,10 @@ k_ppht(u8 *__restrict__ mask, u32 *__restrict__ nz_g, short *__restrict__ accum,
     }
     __syncthreads();
     if (tid == 0) counts[f] = S.nlines;
+    if (trace && tid == 0 && f == 0 && trace_cap >= 2) {  // debug: phase cycles in the last trace record
+        long long *o = (long long *)(trace + (size_t)(trace_cap - 2) * 10);
+        o[0] = dbg_t[0]; o[1] = dbg_t[1]; o[2] = dbg_t[2]; o[3] = dbg_t[3]; o[4] = dbg_picks; o[5] = dbg_votes;
+    }
 }
 
 // debug hook (tests only): record the voting picks of frame 0 -> 10 ints each
@@ -330,6 +346,9 @@ extern "C" int le_hough_lines_p(le_ctx *ctx, const uint8_t *edges, int n, int h,
     k_nz_write<<<dim3(nseg, n), 256, 0, st>>>(edges, segcnt, (u32 *)ctx->ppht_nz.p, (u8 *)ctx->ppht_mask.p,
                                               (int *)ctx->counters.p, npx, nseg, w);
     LE_LAUNCH_CHECK(ctx);
+    if (numangle <= 192 && !getenv("LE_PPHT_GENERIC"))  // batched kernel (le_houghp_fast.cu); same results
+        return le_ppht_fast_launch(ctx, n, h, w, numangle, stride, threshold, min_line_length, max_line_gap, segs,
+                                   counts, max_segs, g_ppht_trace, g_ppht_trace_cap, st);
     LE_CUDA(ctx, cudaMemsetAsync(ctx->ppht_accum.p, 0, sizeof(u16) * (size_t)numangle * stride * n, st));
     LE_T1(ctx, LE_K_PPHT_PREP, st);
     static bool attr = false;
