@@ -109,7 +109,8 @@ static __device__ __forceinline__ int grad_s(const u8 *__restrict__ img, int W, 
 }
 
 __global__ void __launch_bounds__(256) k_lsd_grad(const u8 *__restrict__ img, u32 *__restrict__ ang,
-                                                  int *__restrict__ counters, int H, int W, int s_thr)
+                                                  float2 *__restrict__ cs, int *__restrict__ counters, int H, int W,
+                                                  int s_thr)
 {
     const int f = blockIdx.z;
     const u8 *im = img + (size_t)f * H * W;
@@ -122,8 +123,13 @@ __global__ void __launch_bounds__(256) k_lsd_grad(const u8 *__restrict__ img, u3
             int gx, gy;
             int s = grad_s(im, W, x, y, &gx, &gy);
             if (s > s_thr) {  // sqrt(s/4.0) > rho, threshold resolved on the host in f64
-                out = __float_as_uint(d_fast_atan2((float)gx, (float)-gy));
+                float deg = d_fast_atan2((float)gx, (float)-gy);
+                out = __float_as_uint(deg);
                 smax = s;
+                // cos/sin of the level-line angle exactly as region growing uses them:
+                // cv2 adds cos(float(angle)), sin(float(angle)) to its f32 running sums
+                float af = (float)((double)deg * D2R);
+                cs[(size_t)f * H * W + (size_t)y * W + x] = make_float2((float)cos((double)af), (float)sin((double)af));
             }
         }
         an[(size_t)y * W + x] = out;
@@ -270,14 +276,26 @@ struct LsdRect {
 };
 
 // grow from seed (sx, sy); returns region size.  Warp-uniform; lane k<9 prefetches neighbour k.
-static __device__ int lsd_grow(volatile u32 *an, u32 *reg, int W, int H, int sx, int sy, double tol,
+// One frame is owned by exactly one warp, so its angle plane may live in L1: these loads only have to
+// defeat register caching by the compiler (asm volatile), not the cache (the SM's own stores keep L1 coherent).
+static __device__ __forceinline__ u32 ld_ca(const volatile u32 *p)
+{
+    u32 v;
+    asm volatile("ld.global.ca.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+#define LSD_RING 256  // most recent region points, kept in shared memory for the BFS front
+
+static __device__ int lsd_grow(volatile u32 *an, const float2 *__restrict__ cs, u32 *reg, u32 *ring, int W, int H, int sx, int sy, double tol,
                                double *reg_angle_out, int lane)
 {
     int n = 0;
-    u32 sv = an[(size_t)sy * W + sx] & ~LSD_USED;
+    u32 sv = ld_ca(an + (size_t)sy * W + sx) & ~LSD_USED;
     double reg_angle = (double)__uint_as_float(sv) * D2R;
     if (lane == 0) {
-        reg[0] = ((u32)sy << 16) | (u32)sx;
+        u32 e = ((u32)sy << 16) | (u32)sx;
+        reg[0] = e;
+        ring[0] = e;
         an[(size_t)sy * W + sx] = sv | LSD_USED;
     }
     n = 1;
@@ -285,26 +303,34 @@ static __device__ int lsd_grow(volatile u32 *an, u32 *reg, int W, int H, int sx,
     __syncwarp();
     const int ky = lane / 3 - 1, kx = lane % 3 - 1;
     for (int i = 0; i < n; i++) {
-        u32 pt = ((volatile u32 *)reg)[i];
+        // BFS front: the queue tail is almost always within the shared ring
+        u32 pt = (n - i <= LSD_RING) ? ((volatile u32 *)ring)[i & (LSD_RING - 1)] : ((volatile u32 *)reg)[i];
         int px = (int)(pt & 0xffff), py = (int)(pt >> 16);
         int xx = px + kx, yy = py + ky;
         u32 v = LSD_NOTDEF;
-        if (lane < 9 && xx >= 0 && xx < W && yy >= 0 && yy < H) v = an[(size_t)yy * W + xx];
-#pragma unroll
-        for (int k = 0; k < 9; k++) {
+        float2 csn = make_float2(0.f, 0.f);
+        if (lane < 9 && xx >= 0 && xx < W && yy >= 0 && yy < H) {
+            v = ld_ca(an + (size_t)yy * W + xx);
+            csn = __ldg(cs + (size_t)yy * W + xx);  // read-only plane; garbage where the angle is undefined (never used)
+        }
+        // visit only the neighbours that are defined and free, in (yy, xx) scan order
+        u32 candm = __ballot_sync(~0u, v != LSD_NOTDEF && !(v & LSD_USED)) & 0x1ffu;
+        while (candm) {
+            const int k = __ffs(candm) - 1;
+            candm &= candm - 1;
             u32 vk = __shfl_sync(~0u, v, k);
-            if (vk == LSD_NOTDEF || (vk & LSD_USED)) continue;  // warp-uniform
             double a = (double)__uint_as_float(vk) * D2R;
             if (!aligned_to(reg_angle, a, tol)) continue;
             int ax = px + (k % 3) - 1, ay = py + (k / 3) - 1;
             if (lane == 0) {
+                u32 e = ((u32)ay << 16) | (u32)ax;
                 an[(size_t)ay * W + ax] = vk | LSD_USED;
-                reg[n] = ((u32)ay << 16) | (u32)ax;
+                reg[n] = e;
+                ring[n & (LSD_RING - 1)] = e;
             }
             n++;
-            float af = (float)a;
-            sumdx += (float)cos((double)af);
-            sumdy += (float)sin((double)af);
+            sumdx += __shfl_sync(~0u, csn.x, k);
+            sumdy += __shfl_sync(~0u, csn.y, k);
             reg_angle = (double)d_fast_atan2(sumdy, sumdx) * D2R;
         }
         __syncwarp();
@@ -399,7 +425,7 @@ static __device__ __forceinline__ double dist2d(double x1, double y1, double x2,
 }
 
 // LSD_REFINE_STD (cv2 refine + reduce_region_radius); returns false if the region is rejected
-static __device__ bool lsd_refine(const u8 *__restrict__ im, volatile u32 *an, u32 *reg, int *pn, int W, int H,
+static __device__ bool lsd_refine(const u8 *__restrict__ im, volatile u32 *an, const float2 *__restrict__ cs, u32 *reg, u32 *ring, int *pn, int W, int H,
                                   double *reg_angle, double prec, LsdRect *rec, double density_th, int lane)
 {
     int n = *pn;
@@ -438,7 +464,7 @@ static __device__ bool lsd_refine(const u8 *__restrict__ im, volatile u32 *an, u
     __syncwarp();
     double mean_angle = sum / (double)cnt;
     double tau = 2.0 * sqrt((s_sum - 2.0 * mean_angle * sum) / (double)cnt + mean_angle * mean_angle);
-    n = lsd_grow(an, reg, W, H, sx, sy, tau, reg_angle, lane);
+    n = lsd_grow(an, cs, reg, ring, W, H, sx, sy, tau, reg_angle, lane);
     *pn = n;
     if (n < 2) return false;
     lsd_region2rect(im, reg, n, W, *reg_angle, prec, rec, lane);
@@ -476,6 +502,7 @@ static __device__ bool lsd_refine(const u8 *__restrict__ im, volatile u32 *an, u
 }
 
 __global__ void __launch_bounds__(32) k_lsd_grow(const u8 *__restrict__ img, u32 *__restrict__ ang,
+                                                 const float2 *__restrict__ csbuf,
                                                  const u32 *__restrict__ order, u32 *__restrict__ regbuf,
                                                  const int *__restrict__ counters, LsdParams P,
                                                  float *__restrict__ segs, double *__restrict__ widths,
@@ -486,25 +513,36 @@ __global__ void __launch_bounds__(32) k_lsd_grow(const u8 *__restrict__ img, u32
     const size_t npx = (size_t)H * W;
     const u8 *im = img + (size_t)f * npx;
     volatile u32 *an = ang + (size_t)f * npx;
+    const float2 *cs = csbuf + (size_t)f * npx;
     const u32 *ord = order + (size_t)f * npx;
     u32 *reg = regbuf + (size_t)f * npx;
     const int ndef = counters[f * LE_C_STRIDE + LE_C_AUX0];
     int nseg = 0;
+    __shared__ u32 s_ring[LSD_RING];
     for (int i0 = 0; i0 < ndef; i0 += 32) {
+        // 32 seeds per round: their USED flags are fetched together.  A flag can only flip to USED, so a
+        // seed seen USED is skipped for good; one seen free is re-read only if a region grew since.
         u32 mine = (i0 + lane < ndef) ? ord[i0 + lane] : 0;
+        u32 myv = (i0 + lane < ndef) ? ld_ca(an + mine) : LSD_USED;
+        bool dirty = false;
         int cnt = min(32, ndef - i0);
         for (int j = 0; j < cnt; j++) {
             u32 pidx = __shfl_sync(~0u, mine, j);
-            u32 v = an[pidx];
+            u32 v = __shfl_sync(~0u, myv, j);
             if (v & LSD_USED) continue;  // (NOTDEF has bit 31 set too, but only defined pixels are listed)
+            if (dirty) {
+                v = ld_ca(an + pidx);
+                if (v & LSD_USED) continue;
+            }
+            dirty = true;
             int sy = (int)(pidx / (u32)W), sx = (int)(pidx - (u32)sy * W);
             double reg_angle;
-            int n = lsd_grow(an, reg, W, H, sx, sy, P.prec, &reg_angle, lane);
+            int n = lsd_grow(an, cs, reg, s_ring, W, H, sx, sy, P.prec, &reg_angle, lane);
             if ((unsigned)n < P.min_reg_size) continue;
             LsdRect rec;
             lsd_region2rect(im, reg, n, W, reg_angle, P.prec, &rec, lane);
             if (P.refine > 0) {
-                if (!lsd_refine(im, an, reg, &n, W, H, &reg_angle, P.prec, &rec, P.density_th, lane)) continue;
+                if (!lsd_refine(im, an, cs, reg, s_ring, &n, W, H, &reg_angle, P.prec, &rec, P.density_th, lane)) continue;
             }
             rec.x1 += 0.5; rec.y1 += 0.5; rec.x2 += 0.5; rec.y2 += 0.5;
             if (P.scale != 1) {
@@ -604,6 +642,7 @@ extern "C" int le_lsd(le_ctx *ctx, const uint8_t *gray, int n, int h, int w, int
     if ((rc = le_ensure(ctx, &ctx->lsd2, sizeof(u32) * npx * n))) return rc;                   // angles
     if ((rc = le_ensure(ctx, &ctx->lsd3, sizeof(u32) * npx * n))) return rc;                   // order
     if ((rc = le_ensure(ctx, &ctx->lsd4, sizeof(u32) * npx * n))) return rc;                   // region list
+    if ((rc = le_ensure(ctx, &ctx->lsd6, sizeof(float2) * npx * n))) return rc;                // cos/sin of the angles
     if ((rc = le_ensure(ctx, &ctx->lsd5, (sizeof(u16) + sizeof(u32)) * (size_t)nchunk * n_bins * n + 16))) return rc;
     ctx->edge_list_for = nullptr;
     const u8 *img = gray;
@@ -654,7 +693,8 @@ extern "C" int le_lsd(le_ctx *ctx, const uint8_t *gray, int n, int h, int w, int
     int *cnt = (int *)ctx->counters.p;
     k_lsd_zero<<<(n + 255) / 256, 256, 0, st>>>(cnt, n);
     LE_LAUNCH_CHECK(ctx);
-    k_lsd_grad<<<dim3((W + 31) / 32, (H + 7) / 8, n), 256, 0, st>>>(img, (u32 *)ctx->lsd2.p, cnt, H, W, s_thr);
+    k_lsd_grad<<<dim3((W + 31) / 32, (H + 7) / 8, n), 256, 0, st>>>(img, (u32 *)ctx->lsd2.p, (float2 *)ctx->lsd6.p, cnt, H, W,
+                                                                   s_thr);
     LE_LAUNCH_CHECK(ctx);
     u16 *chist = (u16 *)ctx->lsd5.p;
     u32 *coff = (u32 *)((char *)ctx->lsd5.p + sizeof(u16) * (size_t)nchunk * n_bins * n);
@@ -670,7 +710,8 @@ extern "C" int le_lsd(le_ctx *ctx, const uint8_t *gray, int n, int h, int w, int
     LE_LAUNCH_CHECK(ctx);
     LE_T1(ctx, LE_K_LSD_PREP, st);
     LE_T0(ctx, LE_K_LSD_GROW, st);
-    k_lsd_grow<<<n, 32, 0, st>>>(img, (u32 *)ctx->lsd2.p, (const u32 *)ctx->lsd3.p, (u32 *)ctx->lsd4.p, cnt, P, segs,
+    k_lsd_grow<<<n, 32, 0, st>>>(img, (u32 *)ctx->lsd2.p, (const float2 *)ctx->lsd6.p, (const u32 *)ctx->lsd3.p,
+                                 (u32 *)ctx->lsd4.p, cnt, P, segs,
                                  width, prec_out, counts);
     LE_T1(ctx, LE_K_LSD_GROW, st);
     LE_LAUNCH_CHECK(ctx);
