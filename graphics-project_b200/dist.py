@@ -15,17 +15,31 @@ def shard_range(total, rank, world):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
+_gather_cache = {}
+
+
 def gather_results(counts, payload, total, group=None):
     """All-gather per-frame ``counts`` [b] and padded ``payload`` [b, max_k, ...] from every rank.
 
-    Ranks may own different numbers of frames (block sharding of ``total``); shards are padded to the
-    largest shard for the collective and trimmed afterwards.  Returns (counts [total], payload
-    [total, max_k, ...]) in global frame order on every rank."""
+    Ranks may own different numbers of frames (block sharding of ``total``).  Equal shards (the usual
+    case) go through one ``all_gather_into_tensor`` per array into cached output buffers; ragged shards
+    are padded to the largest shard for the collective and trimmed afterwards.  Returns (counts [total],
+    payload [total, max_k, ...]) in global frame order on every rank (the buffers are reused by the next
+    call with the same shapes)."""
     world = dist.get_world_size(group)
     if world == 1:
         return counts, payload
     sizes = [shard_range(total, r, world)[1] - shard_range(total, r, world)[0] for r in range(world)]
     bmax = max(sizes)
+    if min(sizes) == bmax and counts.shape[0] == bmax:
+        key = (counts.device, counts.dtype, payload.dtype, tuple(payload.shape), world)
+        bufs = _gather_cache.get(key)
+        if bufs is None:
+            bufs = (counts.new_empty((world * bmax,)), payload.new_empty((world * bmax,) + tuple(payload.shape[1:])))
+            _gather_cache[key] = bufs
+        dist.all_gather_into_tensor(bufs[0], counts.contiguous(), group=group)
+        dist.all_gather_into_tensor(bufs[1], payload.contiguous(), group=group)
+        return bufs
     pad = bmax - counts.shape[0]
     if pad:
         counts = torch.cat([counts, counts.new_zeros((pad,))])
