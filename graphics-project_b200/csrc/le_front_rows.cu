@@ -18,8 +18,12 @@
 
 #define FR_STRIP 120
 #define FR_WARPS 1
-#define FR_DEPTH 8  // rows in the cp.async ring (prefetch distance FR_DEPTH - 1)
+#ifndef FR_DEPTH
+#define FR_DEPTH 8
+#endif
+// FR_DEPTH: // rows in the cp.async ring (prefetch distance FR_DEPTH - 1)
 #define FR_FLAT 9  // identical constant rows after which the pipeline state is at its fixed point
+#define FR_STAGE 256  // entries of a warp's strong / weak staging list (a row adds at most 120)
 #ifndef FR_MINBLK
 #define FR_MINBLK 24
 #endif
@@ -124,26 +128,50 @@ static __device__ __noinline__ u32 nms_slow(u32 mul, u32 muh, u32 mml, u32 mmh, 
     return outw;
 }
 
-// strong pixels go to the front of the frame queue, weak candidates to the back (warp-aggregated)
-static __device__ __noinline__ void push_out(u32 outw, u32 pidx0, int *cnt, u32 *q, long long npx)
+// Strong pixels go to the front of the frame queue, weak candidates to the back.  A warp first collects
+// them in its shared staging lists (ballot-compacted, no global traffic) and moves a list to the queue
+// with ONE global atomic once it might not hold another row: the atomic's round trip to L2 was the
+// largest stall of the kernel when it was paid per pixel column.
+struct Stage {
+    u32 *s, *w;   // shared staging lists of this warp: strong, weak
+    int ns, nw;   // entries held (warp-uniform)
+};
+
+static __device__ __forceinline__ void stage_flush(u32 *buf, int &n, int *counter, u32 *q, long long npx, bool back)
 {
     const int lane = threadIdx.x & 31;
+    __syncwarp();
+    int base = 0;
+    if (lane == 0) base = atomicAdd(counter, n);
+    base = __shfl_sync(~0u, base, 0);
+    for (int i = lane; i < n; i += 32) {
+        long long pos = (long long)base + i;
+        q[back ? npx - 1 - pos : pos] = buf[i];
+    }
+    __syncwarp();
+    n = 0;
+}
+
+static __device__ __forceinline__ void stage_push(u32 outw, u32 pidx0, Stage &T)
+{
+    u32 lt;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(lt));
+    const u32 sflag = outw & 0x80808080u;                          // byte == 255
+    const u32 wflag = outw & ~(outw >> 7) & 0x01010101u;           // byte == 1
 #pragma unroll
     for (int k = 0; k < 4; k++) {
-        u32 c = (outw >> (8 * k)) & 255u;
+        const bool pred = (sflag >> (8 * k)) & 0x80u;
+        const u32 b = __ballot_sync(~0u, pred);
+        if (pred) T.s[T.ns + __popc(b & lt)] = pidx0 + k;
+        T.ns += __popc(b);
+    }
+    if (__any_sync(~0u, wflag != 0)) {
 #pragma unroll
-        for (int pass = 0; pass < 2; pass++) {
-            bool pred = pass == 0 ? (c == 255u) : (c == 1u);
-            u32 b = __ballot_sync(~0u, pred);
-            if (b) {
-                int leader = __ffs(b) - 1, base = 0;
-                if (lane == leader) base = atomicAdd(&cnt[pass == 0 ? LE_C_QTAIL : LE_C_WEAK], __popc(b));
-                base = __shfl_sync(~0u, base, leader);
-                if (pred) {
-                    long long pos = (long long)base + __popc(b & ((1u << lane) - 1));
-                    q[pass == 0 ? pos : npx - 1 - pos] = pidx0 + k;
-                }
-            }
+        for (int k = 0; k < 4; k++) {
+            const bool pred = (wflag >> (8 * k)) & 1u;
+            const u32 b = __ballot_sync(~0u, pred);
+            if (pred) T.w[T.nw + __popc(b & lt)] = pidx0 + k;
+            T.nw += __popc(b);
         }
     }
 }
@@ -153,6 +181,7 @@ __global__ void __launch_bounds__(FR_WARPS * 32, FR_MINBLK) k_front_rows(FrontAr
 {
     __shared__ u8 s_lut[LUT ? 256 : 4];
     __shared__ __align__(16) u32 s_ring[FR_WARPS][FR_DEPTH][BGR ? 96 : 32];
+    __shared__ u32 s_stage[FR_WARPS][2][FR_STAGE];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     if (LUT) {
         for (int i = threadIdx.x; i < 256; i += FR_WARPS * 32) s_lut[i] = A.lut[blockIdx.y * 256 + i];
@@ -233,6 +262,9 @@ __global__ void __launch_bounds__(FR_WARPS * 32, FR_MINBLK) k_front_rows(FrontAr
 
     FrontState S;
     memset(&S, 0, sizeof(S));
+    Stage T;
+    T.s = &s_stage[wib][0][0]; T.w = &s_stage[wib][1][0];
+    T.ns = T.nw = 0;
 
     // One pipeline step: consumes the gray word g of input row r, emits the map word of row r - LAGB - 2.
     // lean == true drops every border rule (valid for interior strips and rows away from the image
@@ -302,7 +334,11 @@ __global__ void __launch_bounds__(FR_WARPS * 32, FR_MINBLK) k_front_rows(FrontAr
             if (__any_sync(~0u, S.has_mid)) {
                 outw = nms_slow(S.mul, S.muh, S.mml, S.mmh, ml, mh, S.gxl, S.gxh, S.gyl, S.gyh, S.has_mid, lo, hi);
                 if (!out_lane) outw = 0;
-                if (__any_sync(~0u, outw != 0)) push_out(outw, (u32)(yo * w + x_lane), cnt, q, npx);
+                if (__any_sync(~0u, outw != 0)) {
+                    stage_push(outw, (u32)(yo * w + x_lane), T);
+                    if (T.ns > FR_STAGE - FR_STRIP) stage_flush(T.s, T.ns, &cnt[LE_C_QTAIL], q, npx, false);
+                    if (T.nw > FR_STAGE - FR_STRIP) stage_flush(T.w, T.nw, &cnt[LE_C_WEAK], q, npx, true);
+                }
             }
             if (out_lane) {
                 if (vec_store) *(u32 *)orow = outw;
@@ -372,23 +408,44 @@ __global__ void __launch_bounds__(FR_WARPS * 32, FR_MINBLK) k_front_rows(FrontAr
             };
 #pragma unroll 1
             while (r <= rb) {
+                if (flat >= FR_FLAT && (r & 3) == 0) {
+                    // Four flat rows per trip: the ring slots of rows r..r+3 are consecutive, one vote
+                    // decides for all four, the four freed slots (rows r-1..r+2) are refilled together.
+                    // Output rows are inside the segment here (flat >= FR_FLAT puts r past the warm-up
+                    // rows, rb stops before the rows after the segment), and lean implies w % 4 == 0.
+#pragma unroll 1
+                    while (r + 3 <= rb) {
+                        cp_async_wait<FR_DEPTH - 5>();  // rows r .. r+3 have landed
+                        const u32 *s4 = ring + (r & (FR_DEPTH - 1)) * (ROWB / 4) + lane * WPL;
+                        u32 diff = 0;
+#pragma unroll
+                        for (int k = 0; k < 4; k++) {
+                            diff |= s4[k * (ROWB / 4)] ^ pa;
+                            if (BGR) diff |= (s4[k * (ROWB / 4) + 1] ^ pb) | (s4[k * (ROWB / 4) + 2] ^ pc);
+                        }
+                        if (!__all_sync(~0u, diff == 0)) break;
+#pragma unroll
+                        for (int k = 0; k < 4; k++) refill();
+                        if (out_lane) {
+                            u8 *o = orow;
+#pragma unroll
+                            for (int k = 0; k < 4; k++, o += w) *(u32 *)o = 0u;
+                        }
+                        r += 4;
+                        orow += 4 * (size_t)w;
+                    }
+                    if (r > rb) break;
+                }
                 cp_async_wait<FR_DEPTH - 2>();  // the group of row r has landed
                 const u32 *slot = ring + (r & (FR_DEPTH - 1)) * (ROWB / 4) + lane * WPL;
                 u32 ca = slot[0], cb = BGR ? slot[1] : 0, cc = BGR ? slot[2] : 0;
-                if (flat >= FR_FLAT) {
-                    // tight loop over rows identical to the previous one: nothing but load, compare, store 0
-#pragma unroll 1
-                    while (__all_sync(~0u, ((ca ^ pa) | (cb ^ pb) | (cc ^ pc)) == 0)) {
-                        refill();
-                        if (out_lane && emit_row(r)) *(u32 *)orow = 0u;  // lean implies w % 4 == 0
-                        r++;
-                        orow += w;
-                        if (r > rb) break;
-                        cp_async_wait<FR_DEPTH - 2>();
-                        slot = ring + (r & (FR_DEPTH - 1)) * (ROWB / 4) + lane * WPL;
-                        ca = slot[0]; cb = BGR ? slot[1] : 0; cc = BGR ? slot[2] : 0;
-                    }
-                    if (r > rb) break;
+                if (flat >= FR_FLAT && __all_sync(~0u, ((ca ^ pa) | (cb ^ pb) | (cc ^ pc)) == 0)) {
+                    // one flat row (alignment to a multiple of four, and the rows left over at the end)
+                    refill();
+                    if (out_lane) *(u32 *)orow = 0u;
+                    r++;
+                    orow += w;
+                    continue;
                 }
                 refill();
                 pa = ca; pb = cb; pc = cc;
@@ -409,6 +466,8 @@ __global__ void __launch_bounds__(FR_WARPS * 32, FR_MINBLK) k_front_rows(FrontAr
             cp_async_wait<0>();
         }
     }
+    if (T.ns) stage_flush(T.s, T.ns, &cnt[LE_C_QTAIL], q, npx, false);
+    if (T.nw) stage_flush(T.w, T.nw, &cnt[LE_C_WEAK], q, npx, true);
 }
 
 template <bool BGR, bool BLUR, bool LUT>
