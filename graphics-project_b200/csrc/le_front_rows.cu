@@ -374,7 +374,7 @@ __global__ void __launch_bounds__(FR_WARPS * 32, FR_MINBLK) k_front_rows(FrontAr
         if (phase == 0 && r <= rb) {
             // steady state: rows stream through the cp.async ring, FR_DEPTH - 1 rows ahead
             constexpr int WPL = BGR ? 3 : 1;  // words per lane per row
-            const size_t pitch = (size_t)w * WPL;  // bytes per row
+            const u32 pitch = (u32)w * WPL;  // bytes per row
             const u8 *gp = src + ((size_t)r * w + x_ld) * WPL;
             u32 *ring = &s_ring[wib][0][0];
             const u32 ring_s = (u32)__cvta_generic_to_shared(ring) + lane * WPL * 4;
@@ -406,15 +406,47 @@ __global__ void __launch_bounds__(FR_WARPS * 32, FR_MINBLK) k_front_rows(FrontAr
                 issue_r++;
                 cp_async_commit();
             };
+            const int r_emit = ys + LAGB + 2;  // first input row whose step emits an output row
+            if (r == r0) {
+                // The segment starts here, so the pipeline state is "don't care": the first emitted row
+                // (r0 + 8 with a blur) depends on rows >= r0 only.  If the first row is one constant,
+                // start AT the fixed point of that constant instead of paying nine full warm-up steps
+                // to reach it -- flat strips (most of a cube-edge frame) then never run a full step.
+                cp_async_wait<FR_DEPTH - 2>();
+                const u32 *slot = ring + (r & (FR_DEPTH - 1)) * (ROWB / 4) + lane * WPL;
+                u32 ca = slot[0], cb = BGR ? slot[1] : 0, cc = BGR ? slot[2] : 0;
+                u32 g = BGR ? gray4(ca, cb, cc) : ca;
+                if (xborder) {
+                    u32 gx_ = __shfl_sync(~0u, g, gsx), gy_ = __shfl_sync(~0u, g, gsy);
+                    g = prmt(gx_, gy_, gsel);
+                }
+                int all_eq;
+                __match_all_sync(~0u, g, &all_eq);
+                if (all_eq && g == prmt(g, 0, 0x0000)) {
+                    pa = ca; pb = cb; pc = cc;
+                    gprev = g;
+                    flat = FR_FLAT;
+                    u32 c = g & 255u;
+                    if (LUT) c = s_lut[c];
+                    const u32 P = c * 0x00010001u;
+                    if (BLUR) {
+                        S.a1l = S.a1h = P; S.a2l = S.a2h = 5 * P; S.a3l = S.a3h = 11 * P; S.a4l = S.a4h = 15 * P;
+                    }
+                    S.s1l = S.s1h = P; S.ppl = S.pph = P; S.s2l = S.s2h = 3 * P;
+                    S.gxl = S.gxh = S.gyl = S.gyh = 0x04000400u;
+                    S.mul = S.muh = S.mml = S.mmh = 0u;
+                    S.has_mid = false;
+                }
+            }
 #pragma unroll 1
             while (r <= rb) {
-                if (flat >= FR_FLAT && (r & 3) == 0) {
+                if (flat >= FR_FLAT && (r & 3) == 0 && r >= r_emit) {
                     // Four flat rows per trip: the ring slots of rows r..r+3 are consecutive, one vote
                     // decides for all four, the four freed slots (rows r-1..r+2) are refilled together.
-                    // Output rows are inside the segment here (flat >= FR_FLAT puts r past the warm-up
-                    // rows, rb stops before the rows after the segment), and lean implies w % 4 == 0.
+                    // Output rows are inside the segment here (r >= r_emit, rb stops before the rows
+                    // after the segment), and lean implies w % 4 == 0.
 #pragma unroll 1
-                    while (r + 3 <= rb) {
+                    while (issue_r + 3 <= rb) {
                         cp_async_wait<FR_DEPTH - 5>();  // rows r .. r+3 have landed
                         const u32 *s4 = ring + (r & (FR_DEPTH - 1)) * (ROWB / 4) + lane * WPL;
                         u32 diff = 0;
@@ -424,8 +456,19 @@ __global__ void __launch_bounds__(FR_WARPS * 32, FR_MINBLK) k_front_rows(FrontAr
                             if (BGR) diff |= (s4[k * (ROWB / 4) + 1] ^ pb) | (s4[k * (ROWB / 4) + 2] ^ pc);
                         }
                         if (!__all_sync(~0u, diff == 0)) break;
+                        {   // rows issue_r .. issue_r+3 go to slots (r-1), r, r+1, r+2
+                            const u32 sb = ring_s + (u32)(r & (FR_DEPTH - 1)) * ROWB;
+                            const u32 s0 = ring_s + (u32)((r - 1) & (FR_DEPTH - 1)) * ROWB;
 #pragma unroll
-                        for (int k = 0; k < 4; k++) refill();
+                            for (int j = 0; j < 4; j++) {
+                                const u32 sa = j == 0 ? s0 : sb + (u32)(j - 1) * ROWB;
+#pragma unroll
+                                for (int k = 0; k < WPL; k++) cp_async4(sa + 4 * k, gp + 4 * k);
+                                gp += pitch;
+                                cp_async_commit();
+                            }
+                            issue_r += 4;
+                        }
                         if (out_lane) {
                             u8 *o = orow;
 #pragma unroll
@@ -434,7 +477,6 @@ __global__ void __launch_bounds__(FR_WARPS * 32, FR_MINBLK) k_front_rows(FrontAr
                         r += 4;
                         orow += 4 * (size_t)w;
                     }
-                    if (r > rb) break;
                 }
                 cp_async_wait<FR_DEPTH - 2>();  // the group of row r has landed
                 const u32 *slot = ring + (r & (FR_DEPTH - 1)) * (ROWB / 4) + lane * WPL;
@@ -442,7 +484,7 @@ __global__ void __launch_bounds__(FR_WARPS * 32, FR_MINBLK) k_front_rows(FrontAr
                 if (flat >= FR_FLAT && __all_sync(~0u, ((ca ^ pa) | (cb ^ pb) | (cc ^ pc)) == 0)) {
                     // one flat row (alignment to a multiple of four, and the rows left over at the end)
                     refill();
-                    if (out_lane) *(u32 *)orow = 0u;
+                    if (out_lane && r >= r_emit) *(u32 *)orow = 0u;
                     r++;
                     orow += w;
                     continue;

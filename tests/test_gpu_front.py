@@ -147,3 +147,31 @@ def test_many_weak_candidates_use_bfs_path(engine):
             assert (nms == 1).sum() > 4096
             assert np.array_equal(e[i], ref)
     engine.check()
+
+
+@pytest.mark.parametrize("batch", [1, 100, 300, 600])
+def test_segments_starting_on_flat_rows(engine, batch):
+    """A row segment that starts on constant rows begins at the pipeline's fixed point instead of warming
+    up; sparse dashes and dots at every row offset (relative to the 7/15/30/120-row segments the batch
+    size selects) must still give the oracle's edge map, for BGR and gray input, with and without blur."""
+    h, w = 300, 256
+    rng = np.random.default_rng(batch)
+    uniq = np.full((6, h, w, 3), (242, 153, 128), np.uint8)
+    for f in range(6):
+        for _ in range(40):
+            y, x = int(rng.integers(0, h)), int(rng.integers(0, w - 12))
+            hh, ww = int(rng.integers(1, 4)), int(rng.integers(1, 12))
+            uniq[f, y:y + hh, x:x + ww] = rng.integers(0, 256, 3)
+    uniq[5, 150:] = (10, 20, 30)   # a second constant region: the constant changes mid-frame
+    t = dev(uniq)[torch.arange(batch, device="cuda") % 6]
+    g = np.stack([R.bgr2gray(i) for i in uniq])
+    tg = dev(g)[torch.arange(batch, device="cuda") % 6]
+    for lo, hi, blur in ((5, 10, True), (5, 150, False)):
+        e = engine.front_canny(t, lo, hi, blur=blur)
+        eg = engine.front_canny(tg, lo, hi, blur=blur)
+        for i in range(6):
+            ref = torch.from_numpy(R.canny(R.gauss5(g[i]) if blur else g[i], lo, hi)).cuda()
+            for j in range(i, batch, 6):
+                assert torch.equal(e[j], ref), (batch, lo, hi, blur, j, "bgr")
+                assert torch.equal(eg[j], ref), (batch, lo, hi, blur, j, "gray")
+    engine.check()
