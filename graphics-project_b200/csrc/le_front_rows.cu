@@ -15,6 +15,7 @@
 // Lane l of a strip covers x in [xs + 4l, xs + 4l + 3], xs = 120 * strip - 4; lanes 1..30 produce
 // output, lanes 0 and 31 only provide the +-4 pixel halo (blur 2 + Sobel 1 + NMS 1).
 #include "le_common.cuh"
+#include <cuda.h>
 
 #define FR_STRIP 120
 #define FR_WARPS 1
@@ -23,7 +24,11 @@
 #endif
 // FR_DEPTH: // rows in the cp.async ring (prefetch distance FR_DEPTH - 1)
 #define FR_FLAT 9  // identical constant rows after which the pipeline state is at its fixed point
-#define FR_STAGE 256  // entries of a warp's strong / weak staging list (a row adds at most 120)
+#ifndef FR_NS
+#define FR_NS 4
+#endif
+// FR_NS: stages of 4 rows in the bulk-copy (TMA) ring
+#define FR_STAGE 224  // entries of a warp's strong / weak staging list (a row adds at most 120)
 #ifndef FR_MINBLK
 #define FR_MINBLK 24
 #endif
@@ -65,6 +70,37 @@ static __device__ __forceinline__ void cp_async4(u32 smem_addr, const void *g)
 static __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 static __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// ---- bulk async copies (TMA engine, SASS UBLKCP) completing on an mbarrier
+static __device__ __forceinline__ void mbar_init(u32 bar, u32 count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+static __device__ __forceinline__ void mbar_init_fence()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+static __device__ __forceinline__ void mbar_expect_tx(u32 bar, u32 bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+static __device__ __forceinline__ void tma_load_2d(u32 dst, const CUtensorMap *tm, int x, int y, u32 bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(dst), "l"(tm), "r"(x), "r"(y), "r"(bar)
+                 : "memory");
+}
+static __device__ __forceinline__ void mbar_wait(u32 bar, u32 parity)
+{
+    u32 done;
+    do {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(done)
+                     : "r"(bar), "r"(parity)
+                     : "memory");
+    } while (!done);
+}
 
 struct FrontArgs {
     const u8 *src;
@@ -176,11 +212,16 @@ static __device__ __forceinline__ void stage_push(u32 outw, u32 pidx0, Stage &T)
     }
 }
 
-template <bool BGR, bool BLUR, bool LUT>
-__global__ void __launch_bounds__(FR_WARPS * 32, FR_MINBLK) k_front_rows(FrontArgs A)
+template <bool BGR, bool BLUR, bool LUT, bool TMA>
+__global__ void __launch_bounds__(FR_WARPS * 32, FR_MINBLK) k_front_rows(FrontArgs A, const __grid_constant__ CUtensorMap tmap)
 {
+    // ring row: 128 pixels; the TMA variant copies from the 16-byte boundary below the strip start
+    constexpr int SLOTB = TMA ? (BGR ? 400 : 144) : (BGR ? 384 : 128);
+    constexpr int STAGEB = (4 * SLOTB + 127) / 128 * 128;  // TMA stage: four rows, 128-byte aligned
+    constexpr int RINGW = (TMA ? FR_NS * STAGEB : FR_DEPTH * SLOTB) / 4;
     __shared__ u8 s_lut[LUT ? 256 : 4];
-    __shared__ __align__(16) u32 s_ring[FR_WARPS][FR_DEPTH][BGR ? 96 : 32];
+    __shared__ __align__(128) u32 s_ring[FR_WARPS][RINGW];
+    __shared__ __align__(8) u64 s_bar[FR_WARPS][TMA ? FR_NS : 1];
     __shared__ u32 s_stage[FR_WARPS][2][FR_STAGE];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     if (LUT) {
@@ -372,54 +413,30 @@ __global__ void __launch_bounds__(FR_WARPS * 32, FR_MINBLK) k_front_rows(FrontAr
 #pragma unroll 1
         for (; r <= pe; r++, orow += w) step(load_row(r), r, orow, false, emit_row(r));
         if (phase == 0 && r <= rb) {
-            // steady state: rows stream through the cp.async ring, FR_DEPTH - 1 rows ahead
+            // steady state: rows stream through a per-warp shared-memory ring
             constexpr int WPL = BGR ? 3 : 1;  // words per lane per row
-            const u32 pitch = (u32)w * WPL;  // bytes per row
-            const u8 *gp = src + ((size_t)r * w + x_ld) * WPL;
-            u32 *ring = &s_ring[wib][0][0];
-            const u32 ring_s = (u32)__cvta_generic_to_shared(ring) + lane * WPL * 4;
-            constexpr u32 ROWB = (BGR ? 96 : 32) * 4;
-            int issue_r = r;  // next row to request
-#pragma unroll
-            for (int d = 0; d < FR_DEPTH - 1; d++) {
-                if (issue_r <= rb) {
-                    u32 sa = ring_s + (u32)(issue_r & (FR_DEPTH - 1)) * ROWB;
-#pragma unroll
-                    for (int k = 0; k < WPL; k++) cp_async4(sa + 4 * k, gp + 4 * k);
-                    gp += pitch;
-                }
-                issue_r++;
-                cp_async_commit();
-            }
+            const u32 pitch = (u32)w * WPL;   // bytes per row
+            u32 *ring = &s_ring[wib][0];
             // Flat-row skip: once FR_FLAT consecutive rows of this strip were one constant, every
             // pipeline register sits at its fixed point (partial sums of a constant, zero magnitudes),
             // so a further identical row leaves the state untouched and its output row is zero.
             u32 pa = 0, pb = 0, pc = 0, gprev = 0;
             int flat = 0;
-            auto refill = [&]() {  // request row issue_r into the slot consumed one iteration ago
-                if (issue_r <= rb) {
-                    u32 sa = ring_s + (u32)(issue_r & (FR_DEPTH - 1)) * ROWB;
-#pragma unroll
-                    for (int k = 0; k < WPL; k++) cp_async4(sa + 4 * k, gp + 4 * k);
-                    gp += pitch;
-                }
-                issue_r++;
-                cp_async_commit();
-            };
             const int r_emit = ys + LAGB + 2;  // first input row whose step emits an output row
-            if (r == r0) {
-                // The segment starts here, so the pipeline state is "don't care": the first emitted row
-                // (r0 + 8 with a blur) depends on rows >= r0 only.  If the first row is one constant,
-                // start AT the fixed point of that constant instead of paying nine full warm-up steps
-                // to reach it -- flat strips (most of a cube-edge frame) then never run a full step.
-                cp_async_wait<FR_DEPTH - 2>();
-                const u32 *slot = ring + (r & (FR_DEPTH - 1)) * (ROWB / 4) + lane * WPL;
-                u32 ca = slot[0], cb = BGR ? slot[1] : 0, cc = BGR ? slot[2] : 0;
+            auto gray_of = [&](u32 ca, u32 cb, u32 cc) -> u32 {
                 u32 g = BGR ? gray4(ca, cb, cc) : ca;
-                if (xborder) {
+                if (xborder) {  // warp-uniform
                     u32 gx_ = __shfl_sync(~0u, g, gsx), gy_ = __shfl_sync(~0u, g, gsy);
                     g = prmt(gx_, gy_, gsel);
                 }
+                return g;
+            };
+            // The segment starts at r0, so the pipeline state there is "don't care": the first emitted
+            // row (r0 + 8 with a blur) depends on rows >= r0 only.  If the first row is one constant,
+            // start AT the fixed point of that constant instead of paying nine full warm-up steps to
+            // reach it -- flat strips (most of a cube-edge frame) then never run a full step.
+            auto fixed_start = [&](u32 ca, u32 cb, u32 cc) {
+                const u32 g = gray_of(ca, cb, cc);
                 int all_eq;
                 __match_all_sync(~0u, g, &all_eq);
                 if (all_eq && g == prmt(g, 0, 0x0000)) {
@@ -437,65 +454,10 @@ __global__ void __launch_bounds__(FR_WARPS * 32, FR_MINBLK) k_front_rows(FrontAr
                     S.mul = S.muh = S.mml = S.mmh = 0u;
                     S.has_mid = false;
                 }
-            }
-#pragma unroll 1
-            while (r <= rb) {
-                if (flat >= FR_FLAT && (r & 3) == 0 && r >= r_emit) {
-                    // Four flat rows per trip: the ring slots of rows r..r+3 are consecutive, one vote
-                    // decides for all four, the four freed slots (rows r-1..r+2) are refilled together.
-                    // Output rows are inside the segment here (r >= r_emit, rb stops before the rows
-                    // after the segment), and lean implies w % 4 == 0.
-#pragma unroll 1
-                    while (issue_r + 3 <= rb) {
-                        cp_async_wait<FR_DEPTH - 5>();  // rows r .. r+3 have landed
-                        const u32 *s4 = ring + (r & (FR_DEPTH - 1)) * (ROWB / 4) + lane * WPL;
-                        u32 diff = 0;
-#pragma unroll
-                        for (int k = 0; k < 4; k++) {
-                            diff |= s4[k * (ROWB / 4)] ^ pa;
-                            if (BGR) diff |= (s4[k * (ROWB / 4) + 1] ^ pb) | (s4[k * (ROWB / 4) + 2] ^ pc);
-                        }
-                        if (!__all_sync(~0u, diff == 0)) break;
-                        {   // rows issue_r .. issue_r+3 go to slots (r-1), r, r+1, r+2
-                            const u32 sb = ring_s + (u32)(r & (FR_DEPTH - 1)) * ROWB;
-                            const u32 s0 = ring_s + (u32)((r - 1) & (FR_DEPTH - 1)) * ROWB;
-#pragma unroll
-                            for (int j = 0; j < 4; j++) {
-                                const u32 sa = j == 0 ? s0 : sb + (u32)(j - 1) * ROWB;
-#pragma unroll
-                                for (int k = 0; k < WPL; k++) cp_async4(sa + 4 * k, gp + 4 * k);
-                                gp += pitch;
-                                cp_async_commit();
-                            }
-                            issue_r += 4;
-                        }
-                        if (out_lane) {
-                            u8 *o = orow;
-#pragma unroll
-                            for (int k = 0; k < 4; k++, o += w) *(u32 *)o = 0u;
-                        }
-                        r += 4;
-                        orow += 4 * (size_t)w;
-                    }
-                }
-                cp_async_wait<FR_DEPTH - 2>();  // the group of row r has landed
-                const u32 *slot = ring + (r & (FR_DEPTH - 1)) * (ROWB / 4) + lane * WPL;
-                u32 ca = slot[0], cb = BGR ? slot[1] : 0, cc = BGR ? slot[2] : 0;
-                if (flat >= FR_FLAT && __all_sync(~0u, ((ca ^ pa) | (cb ^ pb) | (cc ^ pc)) == 0)) {
-                    // one flat row (alignment to a multiple of four, and the rows left over at the end)
-                    refill();
-                    if (out_lane && r >= r_emit) *(u32 *)orow = 0u;
-                    r++;
-                    orow += w;
-                    continue;
-                }
-                refill();
+            };
+            auto full_row = [&](u32 ca, u32 cb, u32 cc) {  // one full pipeline step on row r
                 pa = ca; pb = cb; pc = cc;
-                u32 g = BGR ? gray4(ca, cb, cc) : ca;
-                if (xborder) {  // warp-uniform
-                    u32 gx_ = __shfl_sync(~0u, g, gsx), gy_ = __shfl_sync(~0u, g, gsy);
-                    g = prmt(gx_, gy_, gsel);
-                }
+                const u32 g = gray_of(ca, cb, cc);
                 int all_eq;
                 __match_all_sync(~0u, g, &all_eq);
                 const bool row_const = all_eq && g == prmt(g, 0, 0x0000);  // warp-uniform
@@ -504,15 +466,189 @@ __global__ void __launch_bounds__(FR_WARPS * 32, FR_MINBLK) k_front_rows(FrontAr
                 step(g, r, orow, true, emit_row(r));
                 r++;
                 orow += w;
+            };
+            auto zero4 = [&]() {  // four flat output rows (inside the segment; lean implies w % 4 == 0)
+                if (out_lane) {
+                    u8 *o = orow;
+#pragma unroll
+                    for (int k = 0; k < 4; k++, o += w) *(u32 *)o = 0u;
+                }
+                r += 4;
+                orow += 4 * (size_t)w;
+            };
+            if constexpr (TMA) {
+                // TMA ring: FR_NS stages of four rows.  Lane 0 arms the stage's mbarrier with the box size
+                // and issues ONE 2-D tensor copy (four rows x 100 words, starting at the 16-byte boundary
+                // below the strip's first byte; columns/rows outside the batch are zero-filled); the
+                // copy engine moves the bytes -- no LSU work and nothing to wait for per lane -- and
+                // every lane waits on the stage parity.  The loop walks stage by stage.
+                const int xb = (strip * FR_STRIP - 4) * WPL;  // first byte of the strip in the row (may be < 0)
+                const int a0 = xb & ~15;
+                const u32 ring_s = (u32)__cvta_generic_to_shared(ring);
+                const u32 bar_s = (u32)__cvta_generic_to_shared(&s_bar[wib][0]);
+                const u32 *rd = ring + ((xb - a0) >> 2) + lane * WPL;  // this lane's words of ring row 0
+                if (lane == 0) {
+#pragma unroll
+                    for (int i = 0; i < FR_NS; i++) mbar_init(bar_s + 8 * i, 1);
+                    mbar_init_fence();
+                }
+                __syncwarp();
+                int ynext = f * h + r;              // batch row of the next box to request
+                const int ylast = f * h + rb;
+                auto issue = [&](int stg_) {  // request the next four rows into stage stg_
+                    if (lane == 0 && ynext <= ylast) {
+                        const u32 bar = bar_s + 8 * stg_;
+                        mbar_expect_tx(bar, 4 * SLOTB);
+                        tma_load_2d(ring_s + stg_ * STAGEB, &tmap, a0 >> 2, ynext, bar);
+                    }
+                    ynext += 4;
+                };
+#pragma unroll
+                for (int i = 0; i < FR_NS; i++) issue(i);
+                int stg = 0;
+                u32 par = 0;  // parity of the current use of stage stg
+                if (r == r0) {
+                    mbar_wait(bar_s, 0);
+                    fixed_start(rd[0], BGR ? rd[1] : 0, BGR ? rd[2] : 0);
+                }
+#pragma unroll 1
+                while (r <= rb) {
+                    mbar_wait(bar_s + 8 * stg, par);
+                    const u32 *sp = rd + stg * (STAGEB / 4);
+                    bool skip4 = false;
+                    if (flat >= FR_FLAT && r >= r_emit && r + 3 <= rb) {
+                        u32 diff = 0;
+#pragma unroll
+                        for (int k = 0; k < 4; k++) {
+                            diff |= sp[k * (SLOTB / 4)] ^ pa;
+                            if (BGR) diff |= (sp[k * (SLOTB / 4) + 1] ^ pb) | (sp[k * (SLOTB / 4) + 2] ^ pc);
+                        }
+                        skip4 = __all_sync(~0u, diff == 0);
+                    }
+                    if (skip4) {
+                        zero4();
+                    } else {
+                        const int rend = min(r + 3, rb);
+#pragma unroll 1
+                        for (; r <= rend; sp += SLOTB / 4) {
+                            const u32 ca = sp[0], cb = BGR ? sp[1] : 0, cc = BGR ? sp[2] : 0;
+                            if (flat >= FR_FLAT && __all_sync(~0u, ((ca ^ pa) | (cb ^ pb) | (cc ^ pc)) == 0)) {
+                                if (out_lane && r >= r_emit) *(u32 *)orow = 0u;
+                                r++;
+                                orow += w;
+                            } else {
+                                full_row(ca, cb, cc);
+                            }
+                        }
+                    }
+                    // all rows of the stage are consumed (every lane's reads are complete): refill it
+                    __syncwarp();
+                    issue(stg);
+                    if (++stg == FR_NS) { stg = 0; par ^= 1u; }
+                }
+            } else {
+                // cp.async (LDGSTS) ring, one row per commit group, FR_DEPTH - 1 rows ahead
+                const u8 *gp = src + ((size_t)r * w + x_ld) * WPL;
+                const u32 ring_s = (u32)__cvta_generic_to_shared(ring) + lane * WPL * 4;
+                constexpr u32 ROWB = SLOTB;
+                int issue_r = r;  // next row to request
+                auto refill = [&]() {  // request row issue_r into the slot consumed one iteration ago
+                    if (issue_r <= rb) {
+                        u32 sa = ring_s + (u32)(issue_r & (FR_DEPTH - 1)) * ROWB;
+#pragma unroll
+                        for (int k = 0; k < WPL; k++) cp_async4(sa + 4 * k, gp + 4 * k);
+                        gp += pitch;
+                    }
+                    issue_r++;
+                    cp_async_commit();
+                };
+#pragma unroll
+                for (int d = 0; d < FR_DEPTH - 1; d++) refill();
+                if (r == r0) {
+                    cp_async_wait<FR_DEPTH - 2>();
+                    const u32 *slot = ring + (r & (FR_DEPTH - 1)) * (ROWB / 4) + lane * WPL;
+                    fixed_start(slot[0], BGR ? slot[1] : 0, BGR ? slot[2] : 0);
+                }
+#pragma unroll 1
+                while (r <= rb) {
+                    if (flat >= FR_FLAT && (r & 3) == 0 && r >= r_emit) {
+                        // Four flat rows per trip: the ring slots of rows r..r+3 are consecutive, one vote
+                        // decides for all four, the four freed slots (rows r-1..r+2) are refilled together.
+#pragma unroll 1
+                        while (issue_r + 3 <= rb) {
+                            cp_async_wait<FR_DEPTH - 5>();  // rows r .. r+3 have landed
+                            const u32 *s4 = ring + (r & (FR_DEPTH - 1)) * (ROWB / 4) + lane * WPL;
+                            u32 diff = 0;
+#pragma unroll
+                            for (int k = 0; k < 4; k++) {
+                                diff |= s4[k * (ROWB / 4)] ^ pa;
+                                if (BGR) diff |= (s4[k * (ROWB / 4) + 1] ^ pb) | (s4[k * (ROWB / 4) + 2] ^ pc);
+                            }
+                            if (!__all_sync(~0u, diff == 0)) break;
+                            {   // rows issue_r .. issue_r+3 go to slots (r-1), r, r+1, r+2
+                                const u32 sb = ring_s + (u32)(r & (FR_DEPTH - 1)) * ROWB;
+                                const u32 s0 = ring_s + (u32)((r - 1) & (FR_DEPTH - 1)) * ROWB;
+#pragma unroll
+                                for (int j = 0; j < 4; j++) {
+                                    const u32 sa = j == 0 ? s0 : sb + (u32)(j - 1) * ROWB;
+#pragma unroll
+                                    for (int k = 0; k < WPL; k++) cp_async4(sa + 4 * k, gp + 4 * k);
+                                    gp += pitch;
+                                    cp_async_commit();
+                                }
+                                issue_r += 4;
+                            }
+                            zero4();
+                        }
+                    }
+                    cp_async_wait<FR_DEPTH - 2>();  // the group of row r has landed
+                    const u32 *slot = ring + (r & (FR_DEPTH - 1)) * (ROWB / 4) + lane * WPL;
+                    u32 ca = slot[0], cb = BGR ? slot[1] : 0, cc = BGR ? slot[2] : 0;
+                    refill();
+                    if (flat >= FR_FLAT && __all_sync(~0u, ((ca ^ pa) | (cb ^ pb) | (cc ^ pc)) == 0)) {
+                        // one flat row (alignment to a multiple of four, and the rows left over at the end)
+                        if (out_lane && r >= r_emit) *(u32 *)orow = 0u;
+                        r++;
+                        orow += w;
+                        continue;
+                    }
+                    full_row(ca, cb, cc);
+                }
+                cp_async_wait<0>();
             }
-            cp_async_wait<0>();
         }
     }
     if (T.ns) stage_flush(T.s, T.ns, &cnt[LE_C_QTAIL], q, npx, false);
     if (T.nw) stage_flush(T.w, T.nw, &cnt[LE_C_WEAK], q, npx, true);
 }
 
-template <bool BGR, bool BLUR, bool LUT>
+// Tensor map of the input batch for the TMA ring: 2-D, 32-bit elements, [n*h rows][row bytes / 4], box =
+// 4 rows x (SLOTB / 4) words.  cuTensorMapEncodeTiled is taken from the driver at run time (no -lcuda).
+static int make_input_tmap(le_ctx *ctx, CUtensorMap *tm, const u8 *src, int n, int h, int row_bytes, int slot_bytes)
+{
+    typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static encode_fn encode = nullptr;
+    if (!encode) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        LE_CUDA(ctx, cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        if (!fn || qres != cudaDriverEntryPointSuccess) return le_fail(ctx, LE_ERR_CUDA, "cuTensorMapEncodeTiled not available");
+        encode = (encode_fn)fn;
+    }
+    cuuint64_t gdim[2] = {(cuuint64_t)row_bytes / 4, (cuuint64_t)n * h};
+    cuuint64_t gstride[1] = {(cuuint64_t)row_bytes};
+    cuuint32_t box[2] = {(cuuint32_t)slot_bytes / 4, 4};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = encode(tm, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, (void *)src, gdim, gstride, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return le_fail(ctx, LE_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return LE_OK;
+}
+
+template <bool BGR, bool BLUR, bool LUT, bool TMA>
 static int launch_rows_t(le_ctx *ctx, const u8 *src, u8 *edges, int n, int h, int w, int lo, int hi, cudaStream_t st)
 {
     FrontArgs A;
@@ -529,18 +665,41 @@ static int launch_rows_t(le_ctx *ctx, const u8 *src, u8 *edges, int n, int h, in
     int items = A.nstrips * A.nsegs;
     dim3 grid((items + FR_WARPS - 1) / FR_WARPS, n);
     LE_T0(ctx, LE_K_FRONT, st);
-    k_front_rows<BGR, BLUR, LUT><<<grid, FR_WARPS * 32, 0, st>>>(A);
+    static bool carveout_set = false;  // all of the SM's shared memory: 24 one-warp blocks with their rings
+    if (!carveout_set) {
+        cudaFuncSetAttribute(k_front_rows<BGR, BLUR, LUT, TMA>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        carveout_set = true;
+    }
+    CUtensorMap tm;
+    memset(&tm, 0, sizeof(tm));
+    if (TMA) {
+        int rc = make_input_tmap(ctx, &tm, src, n, h, w * (BGR ? 3 : 1), BGR ? 400 : 144);
+        if (rc != LE_OK) return rc;
+    }
+    k_front_rows<BGR, BLUR, LUT, TMA><<<grid, FR_WARPS * 32, 0, st>>>(A, tm);
     LE_T1(ctx, LE_K_FRONT, st);
     LE_LAUNCH_CHECK(ctx);
     return LE_OK;
 }
 
+template <bool TMA>
+static int launch_rows_v(le_ctx *ctx, const u8 *src, int ch, int blur, int lut, u8 *edges, int n, int h, int w, int lo,
+                         int hi, cudaStream_t st)
+{
+    if (lut) return launch_rows_t<false, false, true, TMA>(ctx, src, edges, n, h, w, lo, hi, st);
+    if (ch == 3 && blur) return launch_rows_t<true, true, false, TMA>(ctx, src, edges, n, h, w, lo, hi, st);
+    if (ch == 3) return launch_rows_t<true, false, false, TMA>(ctx, src, edges, n, h, w, lo, hi, st);
+    if (blur) return launch_rows_t<false, true, false, TMA>(ctx, src, edges, n, h, w, lo, hi, st);
+    return launch_rows_t<false, false, false, TMA>(ctx, src, edges, n, h, w, lo, hi, st);
+}
+
 int le_front_rows_launch(le_ctx *ctx, const u8 *src, int ch, int blur, int lut, u8 *edges, int n, int h, int w, int lo,
                          int hi, cudaStream_t st)
 {
-    if (lut) return launch_rows_t<false, false, true>(ctx, src, edges, n, h, w, lo, hi, st);
-    if (ch == 3 && blur) return launch_rows_t<true, true, false>(ctx, src, edges, n, h, w, lo, hi, st);
-    if (ch == 3) return launch_rows_t<true, false, false>(ctx, src, edges, n, h, w, lo, hi, st);
-    if (blur) return launch_rows_t<false, true, false>(ctx, src, edges, n, h, w, lo, hi, st);
-    return launch_rows_t<false, false, false>(ctx, src, edges, n, h, w, lo, hi, st);
+    // Bulk (TMA) copies need 16-byte aligned sources and sizes: rows that are 16-byte multiples on a
+    // 16-byte aligned base.  A ring row starts up to 12 bytes before the strip and ends up to 400 bytes
+    // after its first byte, which must stay inside the frame for rows <= h - 3: w >= 160 covers it.
+    const bool tma = (w % 16) == 0 && w >= 160 && ((uintptr_t)src % 16) == 0 && !getenv("LE_FRONT_NO_TMA");
+    if (tma) return launch_rows_v<true>(ctx, src, ch, blur, lut, edges, n, h, w, lo, hi, st);
+    return launch_rows_v<false>(ctx, src, ch, blur, lut, edges, n, h, w, lo, hi, st);
 }
