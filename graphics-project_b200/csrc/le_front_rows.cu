@@ -123,7 +123,7 @@ struct FrontState {
 
 // Out-of-line NMS + double threshold for the 4 pixels of a lane.  Called warp-convergently.
 // Returns the map word (0 / 1 weak / 255 strong per byte).
-static __device__ __noinline__ u32 nms_slow(u32 mul, u32 muh, u32 mml, u32 mmh, u32 mdl, u32 mdh, u32 gxl, u32 gxh,
+static __device__ __forceinline__ u32 nms_slow(u32 mul, u32 muh, u32 mml, u32 mmh, u32 mdl, u32 mdh, u32 gxl, u32 gxh,
                                             u32 gyl, u32 gyh, int has_mid, int lo, int hi)
 {
     // neighbours' magnitudes of pixel -1 (lane-1, its pixel 3) and pixel 4 (lane+1, its pixel 0)
@@ -169,7 +169,7 @@ static __device__ __noinline__ u32 nms_slow(u32 mul, u32 muh, u32 mml, u32 mmh, 
 // with ONE global atomic once it might not hold another row: the atomic's round trip to L2 was the
 // largest stall of the kernel when it was paid per pixel column.
 struct Stage {
-    u32 *s, *w;   // shared staging lists of this warp: strong, weak
+    u32 *s;       // shared staging lists of this warp: strong at s, weak at s + FR_STAGE
     int ns, nw;   // entries held (warp-uniform)
 };
 
@@ -206,7 +206,7 @@ static __device__ __forceinline__ void stage_push(u32 outw, u32 pidx0, Stage &T)
         for (int k = 0; k < 4; k++) {
             const bool pred = (wflag >> (8 * k)) & 1u;
             const u32 b = __ballot_sync(~0u, pred);
-            if (pred) T.w[T.nw + __popc(b & lt)] = pidx0 + k;
+            if (pred) T.s[FR_STAGE + T.nw + __popc(b & lt)] = pidx0 + k;
             T.nw += __popc(b);
         }
     }
@@ -262,8 +262,9 @@ __global__ void __launch_bounds__(FR_WARPS * 32, FR_MINBLK) k_front_rows(FrontAr
         need_fix = __any_sync(~0u, fix_sel != 0x3210);
     }
     // magnitude is 0 outside the image (per 16-bit half)
-    const u32 mmask01 = ((x_lane >= 0 && x_lane < w) ? 0xffffu : 0u) | ((x_lane + 1 >= 0 && x_lane + 1 < w) ? 0xffff0000u : 0u);
-    const u32 mmask23 = ((x_lane + 2 >= 0 && x_lane + 2 < w) ? 0xffffu : 0u) | ((x_lane + 3 >= 0 && x_lane + 3 < w) ? 0xffff0000u : 0u);
+    u32 mbits = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) mbits |= (x_lane + k >= 0 && x_lane + k < w) ? (1u << k) : 0u;
     const u32 kcmp = (0x7fffu - (u32)lo) * 0x00010001u;
     const bool vec_store = (w & 3) == 0;
 
@@ -279,6 +280,9 @@ __global__ void __launch_bounds__(FR_WARPS * 32, FR_MINBLK) k_front_rows(FrontAr
         else { gsx = gsy = lane - 1 - j; gsel = 0x7777; }
     }
     gsx = min(max(gsx, 0), 31); gsy = min(max(gsy, 0), 31);
+    // everything only border strips need lives in two packed registers (unpacked where used)
+    const u32 bord0 = fix_sel | ((u32)fix_src << 16) | (mbits << 24);
+    const u32 bord1 = gsel | ((u32)gsx << 16) | ((u32)gsy << 24);
     const int x_ld = min(max(x_lane, 0), max(w - 4, 0));  // load position (always inside the row)
 
     // ---- general loader of the gray (or pre-Sobel) word of row r: any lane, any row
@@ -304,7 +308,7 @@ __global__ void __launch_bounds__(FR_WARPS * 32, FR_MINBLK) k_front_rows(FrontAr
     FrontState S;
     memset(&S, 0, sizeof(S));
     Stage T;
-    T.s = &s_stage[wib][0][0]; T.w = &s_stage[wib][1][0];
+    T.s = &s_stage[wib][0][0];
     T.ns = T.nw = 0;
 
     // One pipeline step: consumes the gray word g of input row r, emits the map word of row r - LAGB - 2.
@@ -332,8 +336,8 @@ __global__ void __launch_bounds__(FR_WARPS * 32, FR_MINBLK) k_front_rows(FrontAr
             u32 o23 = vl + R01 + 0x00800080u + 4 * (P12 + P34) + 6 * vh;
             B = prmt(o01, o23, 0x7531);
             if (need_fix) {  // warp-uniform: only strips that touch the left/right image border
-                u32 nbw = __shfl_sync(~0u, B, fix_src);
-                B = prmt(B, nbw, fix_sel);
+                u32 nbw = __shfl_sync(~0u, B, (bord0 >> 16) & 31);
+                B = prmt(B, nbw, bord0 & 0xffffu);
             }
         } else {
             B = g;
@@ -365,7 +369,11 @@ __global__ void __launch_bounds__(FR_WARPS * 32, FR_MINBLK) k_front_rows(FrontAr
             ml = row_in ? ml : 0u;
             mh = row_in ? mh : 0u;
         }
-        if (xborder) { ml &= mmask01; mh &= mmask23; }  // warp-uniform
+        if (xborder) {  // warp-uniform
+            const u32 mb = bord0 >> 24;
+            ml &= ((mb & 1u) ? 0xffffu : 0u) | ((mb & 2u) ? 0xffff0000u : 0u);
+            mh &= ((mb & 4u) ? 0xffffu : 0u) | ((mb & 8u) ? 0xffff0000u : 0u);
+        }
         const bool has_new = ((__vmaxu2(ml, mh) + kcmp) & 0x80008000u) != 0;
 
         // ---- NMS + threshold for row yo = ysob - 1 (magnitude rows: up, mid, new)
@@ -378,7 +386,7 @@ __global__ void __launch_bounds__(FR_WARPS * 32, FR_MINBLK) k_front_rows(FrontAr
                 if (__any_sync(~0u, outw != 0)) {
                     stage_push(outw, (u32)(yo * w + x_lane), T);
                     if (T.ns > FR_STAGE - FR_STRIP) stage_flush(T.s, T.ns, &cnt[LE_C_QTAIL], q, npx, false);
-                    if (T.nw > FR_STAGE - FR_STRIP) stage_flush(T.w, T.nw, &cnt[LE_C_WEAK], q, npx, true);
+                    if (T.nw > FR_STAGE - FR_STRIP) stage_flush(T.s + FR_STAGE, T.nw, &cnt[LE_C_WEAK], q, npx, true);
                 }
             }
             if (out_lane) {
@@ -426,8 +434,8 @@ __global__ void __launch_bounds__(FR_WARPS * 32, FR_MINBLK) k_front_rows(FrontAr
             auto gray_of = [&](u32 ca, u32 cb, u32 cc) -> u32 {
                 u32 g = BGR ? gray4(ca, cb, cc) : ca;
                 if (xborder) {  // warp-uniform
-                    u32 gx_ = __shfl_sync(~0u, g, gsx), gy_ = __shfl_sync(~0u, g, gsy);
-                    g = prmt(gx_, gy_, gsel);
+                    u32 gx_ = __shfl_sync(~0u, g, (bord1 >> 16) & 31), gy_ = __shfl_sync(~0u, g, bord1 >> 24);
+                    g = prmt(gx_, gy_, bord1 & 0xffffu);
                 }
                 return g;
             };
@@ -493,28 +501,29 @@ __global__ void __launch_bounds__(FR_WARPS * 32, FR_MINBLK) k_front_rows(FrontAr
                     mbar_init_fence();
                 }
                 __syncwarp();
-                int ynext = f * h + r;              // batch row of the next box to request
-                const int ylast = f * h + rb;
-                auto issue = [&](int stg_) {  // request the next four rows into stage stg_
-                    if (lane == 0 && ynext <= ylast) {
-                        const u32 bar = bar_s + 8 * stg_;
+                // Stage and parity follow from the row: group gi = (r - ra) / 4 lives in stage gi % FR_NS on
+                // its (gi / FR_NS)-th use -- no loop-carried ring state.
+                const int rs = r;
+                const int ybase = f * h + rs, ylast = f * h + rb;  // batch rows of the first / last ring row
+                auto issue = [&](int gi) {  // request the four rows of group gi into its stage
+                    const int y = ybase + 4 * gi;
+                    if (lane == 0 && y <= ylast) {
+                        const u32 bar = bar_s + 8 * (gi & (FR_NS - 1));
                         mbar_expect_tx(bar, 4 * SLOTB);
-                        tma_load_2d(ring_s + stg_ * STAGEB, &tmap, a0 >> 2, ynext, bar);
+                        tma_load_2d(ring_s + (gi & (FR_NS - 1)) * STAGEB, &tmap, a0 >> 2, y, bar);
                     }
-                    ynext += 4;
                 };
 #pragma unroll
                 for (int i = 0; i < FR_NS; i++) issue(i);
-                int stg = 0;
-                u32 par = 0;  // parity of the current use of stage stg
                 if (r == r0) {
                     mbar_wait(bar_s, 0);
                     fixed_start(rd[0], BGR ? rd[1] : 0, BGR ? rd[2] : 0);
                 }
 #pragma unroll 1
                 while (r <= rb) {
-                    mbar_wait(bar_s + 8 * stg, par);
-                    const u32 *sp = rd + stg * (STAGEB / 4);
+                    const int gi = (r - rs) >> 2;
+                    mbar_wait(bar_s + 8 * (gi & (FR_NS - 1)), (gi / FR_NS) & 1);
+                    const u32 *sp = rd + (gi & (FR_NS - 1)) * (STAGEB / 4);
                     bool skip4 = false;
                     if (flat >= FR_FLAT && r >= r_emit && r + 3 <= rb) {
                         u32 diff = 0;
@@ -528,7 +537,7 @@ __global__ void __launch_bounds__(FR_WARPS * 32, FR_MINBLK) k_front_rows(FrontAr
                     if (skip4) {
                         zero4();
                     } else {
-                        const int rend = min(r + 3, rb);
+                        const int rend = min(rs + 4 * gi + 3, rb);
 #pragma unroll 1
                         for (; r <= rend; sp += SLOTB / 4) {
                             const u32 ca = sp[0], cb = BGR ? sp[1] : 0, cc = BGR ? sp[2] : 0;
@@ -543,8 +552,7 @@ __global__ void __launch_bounds__(FR_WARPS * 32, FR_MINBLK) k_front_rows(FrontAr
                     }
                     // all rows of the stage are consumed (every lane's reads are complete): refill it
                     __syncwarp();
-                    issue(stg);
-                    if (++stg == FR_NS) { stg = 0; par ^= 1u; }
+                    issue(gi + FR_NS);
                 }
             } else {
                 // cp.async (LDGSTS) ring, one row per commit group, FR_DEPTH - 1 rows ahead
@@ -619,7 +627,7 @@ __global__ void __launch_bounds__(FR_WARPS * 32, FR_MINBLK) k_front_rows(FrontAr
         }
     }
     if (T.ns) stage_flush(T.s, T.ns, &cnt[LE_C_QTAIL], q, npx, false);
-    if (T.nw) stage_flush(T.w, T.nw, &cnt[LE_C_WEAK], q, npx, true);
+    if (T.nw) stage_flush(T.s + FR_STAGE, T.nw, &cnt[LE_C_WEAK], q, npx, true);
 }
 
 // Tensor map of the input batch for the TMA ring: 2-D, 32-bit elements, [n*h rows][row bytes / 4], box =
