@@ -60,7 +60,7 @@ extern "C" int le_create(le_ctx **out, int device, int max_h, int max_w, int max
     cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
     cudaDeviceGetAttribute(&ctx->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     if (max_h > 0 && max_w > 0 && max_batch > 0) {
-        int rc = le_ensure(ctx, &ctx->counters, sizeof(int) * LE_C_STRIDE * (size_t)max_batch);
+        int rc = le_ensure(ctx, &ctx->counters, sizeof(int) * LE_C_STRIDE * ((size_t)max_batch + 1));
         if (rc == LE_OK) rc = le_ensure(ctx, &ctx->queue, sizeof(u32) * (size_t)max_batch * max_h * max_w);
         if (rc != LE_OK) {
             strncpy(g_create_err, ctx->err, 511);

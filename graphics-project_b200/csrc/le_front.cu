@@ -438,13 +438,13 @@ __global__ void __launch_bounds__(256) k_edge_list(const u8 *__restrict__ map, u
 __global__ void k_zero_counters(int *counters, int n)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n * LE_C_STRIDE) counters[i] = 0;
+    if (i < (n + 1) * LE_C_STRIDE) counters[i] = 0;  // group n: launch-wide counters (front work items)
 }
 
 // ------------------------------------------------------------------ host side
 static int front_scratch(le_ctx *ctx, int n, int h, int w)
 {
-    int rc = le_ensure(ctx, &ctx->counters, sizeof(int) * LE_C_STRIDE * (size_t)n);
+    int rc = le_ensure(ctx, &ctx->counters, sizeof(int) * LE_C_STRIDE * ((size_t)n + 1));
     if (rc) return rc;
     return le_ensure(ctx, &ctx->queue, sizeof(u32) * (size_t)n * h * w);
 }
@@ -484,7 +484,7 @@ extern "C" int le_gauss5_u8(le_ctx *ctx, const uint8_t *src, uint8_t *dst, int n
 
 static int minmax_lut(le_ctx *ctx, const u8 *src, int n, int h, int w, cudaStream_t st)
 {
-    int rc = le_ensure(ctx, &ctx->counters, sizeof(int) * LE_C_STRIDE * (size_t)n);
+    int rc = le_ensure(ctx, &ctx->counters, sizeof(int) * LE_C_STRIDE * ((size_t)n + 1));
     if (rc) return rc;
     rc = le_ensure(ctx, &ctx->lut, 256 * (size_t)n);
     if (rc) return rc;
@@ -566,7 +566,7 @@ int le_front_launch(le_ctx *ctx, const u8 *src, int ch, int do_blur, int do_norm
         in_ch = 1;
         blur = 0;
     }
-    k_zero_counters<<<(n * LE_C_STRIDE + 255) / 256, 256, 0, st>>>((int *)ctx->counters.p, n);
+    k_zero_counters<<<((n + 1) * LE_C_STRIDE + 255) / 256, 256, 0, st>>>((int *)ctx->counters.p, n);
     LE_LAUNCH_CHECK(ctx);
     if (getenv("LE_FRONT_V1")) {  // previous shared-memory tile kernel, kept for A/B measurements only
         if (do_norm) rc = launch_front_t<false, false, true>(ctx, in, edges, n, h, w, lo, hi, st);
@@ -627,7 +627,7 @@ int le_edge_list_from_map(le_ctx *ctx, const u8 *edges, int n, int h, int w, cud
     }
     int rc = front_scratch(ctx, n, h, w);
     if (rc) return rc;
-    k_zero_counters<<<(n * LE_C_STRIDE + 255) / 256, 256, 0, st>>>((int *)ctx->counters.p, n);
+    k_zero_counters<<<((n + 1) * LE_C_STRIDE + 255) / 256, 256, 0, st>>>((int *)ctx->counters.p, n);
     LE_LAUNCH_CHECK(ctx);
     size_t npx = (size_t)h * w;
     int bx = (int)min((size_t)128, (npx + 255) / 256);

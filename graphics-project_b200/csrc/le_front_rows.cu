@@ -110,6 +110,8 @@ struct FrontArgs {
     const u8 *lut;
     int h, w, lo, hi;
     int rows_per_seg, nstrips, nsegs;
+    int *work;    // work-item counter of this launch (zeroed before it)
+    int nframes;
 };
 
 // Pipeline state of one lane (packed 16-bit pairs: l = pixels 0,1; h = pixels 2,3)
@@ -224,17 +226,37 @@ __global__ void __launch_bounds__(FR_WARPS * 32, FR_MINBLK) k_front_rows(FrontAr
     __shared__ __align__(8) u64 s_bar[FR_WARPS][TMA ? FR_NS : 1];
     __shared__ u32 s_stage[FR_WARPS][2][FR_STAGE];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    if (LUT) {
-        for (int i = threadIdx.x; i < 256; i += FR_WARPS * 32) s_lut[i] = A.lut[blockIdx.y * 256 + i];
-        __syncthreads();
-    }
-    // work item of this warp: (frame f = blockIdx.y, segment, strip)
-    const int f = blockIdx.y;
-    const int wi = blockIdx.x * FR_WARPS + wib;
-    if (wi >= A.nstrips * A.nsegs) return;
-    const int strip = wi % A.nstrips, seg = wi / A.nstrips;
     const int h = A.h, w = A.w, lo = A.lo, hi = A.hi;
     const long long npx = (long long)h * w;
+    const u32 bar_s = (u32)__cvta_generic_to_shared(&s_bar[wib][0]);
+    if (TMA) {
+        if (lane == 0) {
+#pragma unroll
+            for (int i = 0; i < FR_NS; i++) mbar_init(bar_s + 8 * i, 1);
+            mbar_init_fence();
+        }
+        __syncwarp();
+    }
+    u32 gbase = 0;  // TMA ring: four-row groups this warp has requested (and consumed) so far
+    int lut_frame = -1;
+    // Persistent warps: work items (frame, segment, strip) are handed out by an atomic counter, so a warp
+    // that drew flat strips simply takes more of them and no SM waits for block launches.
+    const int items_per_frame = A.nstrips * A.nsegs;
+#pragma unroll 1
+    for (;;) {
+    int item = 0;
+    if (lane == 0) item = atomicAdd(A.work, 1);
+    item = __shfl_sync(~0u, item, 0);
+    if (item >= items_per_frame * A.nframes) break;
+    const int f = item / items_per_frame;
+    const int wi = item - f * items_per_frame;
+    if (LUT && f != lut_frame) {  // FR_WARPS == 1: the block is this warp
+        __syncwarp();
+        for (int i = lane; i < 256; i += 32) s_lut[i] = A.lut[f * 256 + i];
+        __syncwarp();
+        lut_frame = f;
+    }
+    const int strip = wi % A.nstrips, seg = wi / A.nstrips;
     const u8 *__restrict__ src = A.src + (size_t)f * npx * (BGR ? 3 : 1);
     u8 *__restrict__ map = A.map + (size_t)f * npx;
     u32 *q = A.queue + (size_t)f * npx;
@@ -443,6 +465,18 @@ __global__ void __launch_bounds__(FR_WARPS * 32, FR_MINBLK) k_front_rows(FrontAr
             // row (r0 + 8 with a blur) depends on rows >= r0 only.  If the first row is one constant,
             // start AT the fixed point of that constant instead of paying nine full warm-up steps to
             // reach it -- flat strips (most of a cube-edge frame) then never run a full step.
+            auto set_fixed = [&](u32 g) {  // pipeline state after >= FR_FLAT rows of the constant word g
+                u32 c = g & 255u;
+                if (LUT) c = s_lut[c];
+                const u32 P = c * 0x00010001u;
+                if (BLUR) {
+                    S.a1l = S.a1h = P; S.a2l = S.a2h = 5 * P; S.a3l = S.a3h = 11 * P; S.a4l = S.a4h = 15 * P;
+                }
+                S.s1l = S.s1h = P; S.ppl = S.pph = P; S.s2l = S.s2h = 3 * P;
+                S.gxl = S.gxh = S.gyl = S.gyh = 0x04000400u;
+                S.mul = S.muh = S.mml = S.mmh = 0u;
+                S.has_mid = false;
+            };
             auto fixed_start = [&](u32 ca, u32 cb, u32 cc) {
                 const u32 g = gray_of(ca, cb, cc);
                 int all_eq;
@@ -451,16 +485,7 @@ __global__ void __launch_bounds__(FR_WARPS * 32, FR_MINBLK) k_front_rows(FrontAr
                     pa = ca; pb = cb; pc = cc;
                     gprev = g;
                     flat = FR_FLAT;
-                    u32 c = g & 255u;
-                    if (LUT) c = s_lut[c];
-                    const u32 P = c * 0x00010001u;
-                    if (BLUR) {
-                        S.a1l = S.a1h = P; S.a2l = S.a2h = 5 * P; S.a3l = S.a3h = 11 * P; S.a4l = S.a4h = 15 * P;
-                    }
-                    S.s1l = S.s1h = P; S.ppl = S.pph = P; S.s2l = S.s2h = 3 * P;
-                    S.gxl = S.gxh = S.gyl = S.gyh = 0x04000400u;
-                    S.mul = S.muh = S.mml = S.mmh = 0u;
-                    S.has_mid = false;
+                    if (!TMA) set_fixed(g);  // (the TMA loop rebuilds the state when it leaves flat mode)
                 }
             };
             auto full_row = [&](u32 ca, u32 cb, u32 cc) {  // one full pipeline step on row r
@@ -489,71 +514,84 @@ __global__ void __launch_bounds__(FR_WARPS * 32, FR_MINBLK) k_front_rows(FrontAr
                 // and issues ONE 2-D tensor copy (four rows x 100 words, starting at the 16-byte boundary
                 // below the strip's first byte; columns/rows outside the batch are zero-filled); the
                 // copy engine moves the bytes -- no LSU work and nothing to wait for per lane -- and
-                // every lane waits on the stage parity.  The loop walks stage by stage.
+                // every lane waits on the stage parity.  Stage and parity follow from the row: ring row
+                // k = r - rs belongs to group gbase + k / 4, which lives in stage (group % FR_NS) on its
+                // (group / FR_NS)-th use -- no loop-carried ring state besides gbase.
                 const int xb = (strip * FR_STRIP - 4) * WPL;  // first byte of the strip in the row (may be < 0)
                 const int a0 = xb & ~15;
                 const u32 ring_s = (u32)__cvta_generic_to_shared(ring);
-                const u32 bar_s = (u32)__cvta_generic_to_shared(&s_bar[wib][0]);
                 const u32 *rd = ring + ((xb - a0) >> 2) + lane * WPL;  // this lane's words of ring row 0
-                if (lane == 0) {
-#pragma unroll
-                    for (int i = 0; i < FR_NS; i++) mbar_init(bar_s + 8 * i, 1);
-                    mbar_init_fence();
-                }
-                __syncwarp();
-                // Stage and parity follow from the row: group gi = (r - ra) / 4 lives in stage gi % FR_NS on
-                // its (gi / FR_NS)-th use -- no loop-carried ring state.
                 const int rs = r;
                 const int ybase = f * h + rs, ylast = f * h + rb;  // batch rows of the first / last ring row
-                auto issue = [&](int gi) {  // request the four rows of group gi into its stage
-                    const int y = ybase + 4 * gi;
+                auto issue = [&](u32 k4) {  // request ring rows 4 * k4 .. 4 * k4 + 3
+                    const int y = ybase + 4 * (int)k4;
                     if (lane == 0 && y <= ylast) {
-                        const u32 bar = bar_s + 8 * (gi & (FR_NS - 1));
-                        mbar_expect_tx(bar, 4 * SLOTB);
-                        tma_load_2d(ring_s + (gi & (FR_NS - 1)) * STAGEB, &tmap, a0 >> 2, y, bar);
+                        const u32 stg = (gbase + k4) & (FR_NS - 1);
+                        mbar_expect_tx(bar_s + 8 * stg, 4 * SLOTB);
+                        tma_load_2d(ring_s + stg * STAGEB, &tmap, a0 >> 2, y, bar_s + 8 * stg);
                     }
+                };
+                auto acquire = [&](u32 k4) -> const u32 * {  // wait for group k4, return this lane's words
+                    const u32 G = gbase + k4, stg = G & (FR_NS - 1);
+                    mbar_wait(bar_s + 8 * stg, (G / FR_NS) & 1u);
+                    return rd + stg * (STAGEB / 4);
                 };
 #pragma unroll
                 for (int i = 0; i < FR_NS; i++) issue(i);
                 if (r == r0) {
-                    mbar_wait(bar_s, 0);
-                    fixed_start(rd[0], BGR ? rd[1] : 0, BGR ? rd[2] : 0);
+                    const u32 *sp = acquire(0);
+                    fixed_start(sp[0], BGR ? sp[1] : 0, BGR ? sp[2] : 0);
                 }
 #pragma unroll 1
                 while (r <= rb) {
-                    const int gi = (r - rs) >> 2;
-                    mbar_wait(bar_s + 8 * (gi & (FR_NS - 1)), (gi / FR_NS) & 1);
-                    const u32 *sp = rd + (gi & (FR_NS - 1)) * (STAGEB / 4);
-                    bool skip4 = false;
-                    if (flat >= FR_FLAT && r >= r_emit && r + 3 <= rb) {
-                        u32 diff = 0;
-#pragma unroll
-                        for (int k = 0; k < 4; k++) {
-                            diff |= sp[k * (SLOTB / 4)] ^ pa;
-                            if (BGR) diff |= (sp[k * (SLOTB / 4) + 1] ^ pb) | (sp[k * (SLOTB / 4) + 2] ^ pc);
-                        }
-                        skip4 = __all_sync(~0u, diff == 0);
-                    }
-                    if (skip4) {
-                        zero4();
-                    } else {
-                        const int rend = min(rs + 4 * gi + 3, rb);
+                    if (flat >= FR_FLAT) {
+                        // ---- flat mode: the pipeline state is the fixed point of the constant gprev and is
+                        // not touched (nor kept in registers) here; it is rebuilt when the mode ends.
 #pragma unroll 1
-                        for (; r <= rend; sp += SLOTB / 4) {
+                        while (r <= rb) {
+                            const u32 k = (u32)(r - rs);
+                            const u32 *sp = acquire(k >> 2);
+                            if ((k & 3u) == 0 && r >= r_emit && r + 3 <= rb) {
+                                u32 diff = 0;
+#pragma unroll
+                                for (int j = 0; j < 4; j++) {
+                                    diff |= sp[j * (SLOTB / 4)] ^ pa;
+                                    if (BGR) diff |= (sp[j * (SLOTB / 4) + 1] ^ pb) | (sp[j * (SLOTB / 4) + 2] ^ pc);
+                                }
+                                if (__all_sync(~0u, diff == 0)) {  // four flat rows: the whole stage at once
+                                    zero4();
+                                    __syncwarp();
+                                    issue((k >> 2) + FR_NS);
+                                    continue;
+                                }
+                            }
+                            sp += (k & 3u) * (SLOTB / 4);
                             const u32 ca = sp[0], cb = BGR ? sp[1] : 0, cc = BGR ? sp[2] : 0;
-                            if (flat >= FR_FLAT && __all_sync(~0u, ((ca ^ pa) | (cb ^ pb) | (cc ^ pc)) == 0)) {
-                                if (out_lane && r >= r_emit) *(u32 *)orow = 0u;
-                                r++;
-                                orow += w;
-                            } else {
-                                full_row(ca, cb, cc);
+                            if (!__all_sync(~0u, ((ca ^ pa) | (cb ^ pb) | (cc ^ pc)) == 0)) break;
+                            if (out_lane && r >= r_emit) *(u32 *)orow = 0u;
+                            r++;
+                            orow += w;
+                            if ((k & 3u) == 3u) {
+                                __syncwarp();
+                                issue((k >> 2) + FR_NS);
                             }
                         }
+                        set_fixed(gprev);  // (also when the ring rows are used up: the rows after them run full steps)
+                        if (r > rb) break;
                     }
-                    // all rows of the stage are consumed (every lane's reads are complete): refill it
-                    __syncwarp();
-                    issue(gi + FR_NS);
+                    // ---- full steps until the strip has been flat for FR_FLAT rows again
+#pragma unroll 1
+                    do {
+                        const u32 k = (u32)(r - rs);
+                        const u32 *sp = acquire(k >> 2) + (k & 3u) * (SLOTB / 4);
+                        full_row(sp[0], BGR ? sp[1] : 0, BGR ? sp[2] : 0);
+                        if ((k & 3u) == 3u) {
+                            __syncwarp();
+                            issue((k >> 2) + FR_NS);
+                        }
+                    } while (r <= rb && flat < FR_FLAT);
                 }
+                gbase += (u32)(rb - rs + 4) >> 2;  // groups of this item (all requested, all consumed)
             } else {
                 // cp.async (LDGSTS) ring, one row per commit group, FR_DEPTH - 1 rows ahead
                 const u8 *gp = src + ((size_t)r * w + x_ld) * WPL;
@@ -628,6 +666,7 @@ __global__ void __launch_bounds__(FR_WARPS * 32, FR_MINBLK) k_front_rows(FrontAr
     }
     if (T.ns) stage_flush(T.s, T.ns, &cnt[LE_C_QTAIL], q, npx, false);
     if (T.nw) stage_flush(T.s + FR_STAGE, T.nw, &cnt[LE_C_WEAK], q, npx, true);
+    }  // work items
 }
 
 // Tensor map of the input batch for the TMA ring: 2-D, 32-bit elements, [n*h rows][row bytes / 4], box =
@@ -670,8 +709,10 @@ static int launch_rows_t(le_ctx *ctx, const u8 *src, u8 *edges, int n, int h, in
     while (rows > 8 && (long long)n * A.nstrips * ((h + rows - 1) / rows) < target_warps) rows /= 2;
     A.rows_per_seg = rows;
     A.nsegs = (h + rows - 1) / rows;
-    int items = A.nstrips * A.nsegs;
-    dim3 grid((items + FR_WARPS - 1) / FR_WARPS, n);
+    A.nframes = n;
+    A.work = (int *)ctx->counters.p + (size_t)n * LE_C_STRIDE;  // zeroed with the frame counters
+    long long items = (long long)A.nstrips * A.nsegs * n;
+    dim3 grid((unsigned)min(items, (long long)ctx->sm_count * FR_MINBLK));
     LE_T0(ctx, LE_K_FRONT, st);
     static bool carveout_set = false;  // all of the SM's shared memory: 24 one-warp blocks with their rings
     if (!carveout_set) {
