@@ -112,6 +112,8 @@ struct FrontArgs {
     int rows_per_seg, nstrips, nsegs;
     int *work;    // work-item counter of this launch (zeroed before it)
     int nframes;
+    // the last frames of a big batch are cut into shorter segments so that the final work items are small
+    int tail_frame0, tail_rows_per_seg, tail_nsegs;
 };
 
 // Pipeline state of one lane (packed 16-bit pairs: l = pixels 0,1; h = pixels 2,3)
@@ -241,15 +243,20 @@ __global__ void __launch_bounds__(FR_WARPS * 32, FR_MINBLK) k_front_rows(FrontAr
     int lut_frame = -1;
     // Persistent warps: work items (frame, segment, strip) are handed out by an atomic counter, so a warp
     // that drew flat strips simply takes more of them and no SM waits for block launches.
-    const int items_per_frame = A.nstrips * A.nsegs;
+    const int items_main = A.nstrips * A.nsegs * A.tail_frame0;
+    const int items_all = items_main + A.nstrips * A.tail_nsegs * (A.nframes - A.tail_frame0);
 #pragma unroll 1
     for (;;) {
     int item = 0;
     if (lane == 0) item = atomicAdd(A.work, 1);
     item = __shfl_sync(~0u, item, 0);
-    if (item >= items_per_frame * A.nframes) break;
-    const int f = item / items_per_frame;
-    const int wi = item - f * items_per_frame;
+    if (item >= items_all) break;
+    const bool tail = item >= items_main;
+    const int rows_per_seg = tail ? A.tail_rows_per_seg : A.rows_per_seg;
+    const int items_per_frame = A.nstrips * (tail ? A.tail_nsegs : A.nsegs);
+    if (tail) item -= items_main;
+    const int f = item / items_per_frame + (tail ? A.tail_frame0 : 0);
+    const int wi = item % items_per_frame;
     if (LUT && f != lut_frame) {  // FR_WARPS == 1: the block is this warp
         __syncwarp();
         for (int i = lane; i < 256; i += 32) s_lut[i] = A.lut[f * 256 + i];
@@ -262,7 +269,7 @@ __global__ void __launch_bounds__(FR_WARPS * 32, FR_MINBLK) k_front_rows(FrontAr
     u32 *q = A.queue + (size_t)f * npx;
     int *cnt = A.counters + f * LE_C_STRIDE;
 
-    const int ys = seg * A.rows_per_seg, ye = min(h, ys + A.rows_per_seg);
+    const int ys = seg * rows_per_seg, ye = min(h, ys + rows_per_seg);
     const int x_lane = strip * FR_STRIP - 4 + 4 * lane;  // first pixel of this lane's word
     const bool inside = x_lane >= 0 && x_lane + 3 < w;   // whole word inside the image
     const bool fast_rows = (w & 3) == 0;                 // rows are word aligned (BGR: 3w % 4 == 0 too)
@@ -711,7 +718,13 @@ static int launch_rows_t(le_ctx *ctx, const u8 *src, u8 *edges, int n, int h, in
     A.nsegs = (h + rows - 1) / rows;
     A.nframes = n;
     A.work = (int *)ctx->counters.p + (size_t)n * LE_C_STRIDE;  // zeroed with the frame counters
-    long long items = (long long)A.nstrips * A.nsegs * n;
+    A.tail_frame0 = n; A.tail_rows_per_seg = rows; A.tail_nsegs = A.nsegs;
+    if (n >= 16 && rows >= 60) {  // about the last tenth of the frames: quarter-length segments
+        A.tail_frame0 = n - (n + 9) / 10;
+        A.tail_rows_per_seg = rows / 4;
+        A.tail_nsegs = (h + A.tail_rows_per_seg - 1) / A.tail_rows_per_seg;
+    }
+    long long items = (long long)A.nstrips * (A.nsegs * (long long)A.tail_frame0 + A.tail_nsegs * (long long)(n - A.tail_frame0));
     dim3 grid((unsigned)min(items, (long long)ctx->sm_count * FR_MINBLK));
     LE_T0(ctx, LE_K_FRONT, st);
     static bool carveout_set = false;  // all of the SM's shared memory: 24 one-warp blocks with their rings
