@@ -725,7 +725,9 @@ static int launch_rows_t(le_ctx *ctx, const u8 *src, u8 *edges, int n, int h, in
         A.tail_nsegs = (h + A.tail_rows_per_seg - 1) / A.tail_rows_per_seg;
     }
     long long items = (long long)A.nstrips * (A.nsegs * (long long)A.tail_frame0 + A.tail_nsegs * (long long)(n - A.tail_frame0));
-    dim3 grid((unsigned)min(items, (long long)ctx->sm_count * FR_MINBLK));
+    int per_sm = FR_MINBLK;
+    if (const char *e = getenv("LE_FRONT_BLOCKS_PER_SM")) per_sm = max(1, min(FR_MINBLK, atoi(e)));  // A/B measurements
+    dim3 grid((unsigned)min(items, (long long)ctx->sm_count * per_sm));
     LE_T0(ctx, LE_K_FRONT, st);
     static bool carveout_set = false;  // all of the SM's shared memory: 24 one-warp blocks with their rings
     if (!carveout_set) {

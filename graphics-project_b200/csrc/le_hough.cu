@@ -99,7 +99,7 @@ k_hough_vote(const u32 *__restrict__ queue, int *__restrict__ counters, const fl
 {
     extern __shared__ __align__(16) u32 hist[];  // [A][stride/2]
     __shared__ int s_rlo[A];
-    __shared__ float2 s_stage[HV_THREADS / 32][32];
+    __shared__ __align__(16) float2 s_stage[HV_THREADS / 32][32];
     const int f = blockIdx.y;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nwarps = HV_THREADS / 32;
@@ -142,37 +142,49 @@ k_hough_vote(const u32 *__restrict__ queue, int *__restrict__ counters, const fl
         tsin = trig[numangle + n_mine];
         rlo = row_origin(n_mine);
     }
-    // 32-bit shared address of this lane's row; lanes of rows outside [0, numangle) add 0 (branch-free)
+    // 32-bit shared address of this lane's row.  Lanes of rows outside [0, numangle) (halo of the first /
+    // last stripe) have cos = sin = 0 and vote into bin 0 of their own scratch row, which nobody reads.
     const u32 row_sa = (u32)__cvta_generic_to_shared(hist + a * hw);
-    const u32 one = row_ok ? 1u : 0u;
-    float2 *stage = s_stage[warp];
+    // round-half-even by the magic-number add: bits(v + 1.5 * 2^23) - 0x4B400000 == rint(v) for |v| < 2^22,
+    // the same integer __float2int_rn gives; the row origin is folded into the constant
+    const float MAGIC = 12582912.f;
+    // byte address of bin b (two u16 bins per word): row_sa + 2 * (b - rlo) with bit 1 cleared; bit 1 says
+    // which half of the word.  row_sa is a multiple of 8, so it can ride in the multiply-add's constant.
+    const u32 kbase = row_sa - 2u * (u32)(0x4B400000 + rlo);
+    float4 *stage = (float4 *)s_stage[warp];  // two staged pixels (x0, y0, x1, y1) per entry
+    const float rw = 1.0f / (float)w;
+    auto vote = [&](float x, float y, bool on) {
+        const float t = __fadd_rn(__fadd_rn(__fmul_rn(x, tcos), __fmul_rn(y, tsin)), MAGIC);
+        const u32 s2 = (u32)__float_as_int(t) * 2u + kbase;
+        const u32 val = on ? ((s2 & 2u) ? 0x10000u : 1u) : 0u;
+        asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(s2 & ~2u), "r"(val) : "memory");
+    };
     __syncthreads();
     for (int base = warp * 32; base < nedge; base += nwarps * 32) {
         // each lane converts one queue entry to float (x, y) and stages it; the warp then votes the
-        // 32 pixels with one broadcast LDS.64 per pixel (per PPW pixels when A < 32)
+        // 32 pixels, two per broadcast LDS.128 (lanes = angles, so no two lanes share a row)
         int idx = base + lane;
         int p = idx < nedge ? (int)q[idx] : 0;
-        int py = p / w;
+        int py = (int)((float)p * rw);  // estimate of p / w, then exact correction
+        int px = p - py * w;
+        while (px < 0) { px += w; py--; }
+        while (px >= w) { px -= w; py++; }
         __syncwarp();
-        stage[lane] = make_float2((float)(p - py * w), (float)py);
+        s_stage[warp][lane] = make_float2((float)px, (float)py);
         __syncwarp();
         const int cntw = min(32, nedge - base);
         if (cntw == 32) {
-#pragma unroll 8
-            for (int j = 0; j < 32; j += PPW) {
-                float2 xy = stage[j + sub];
-                int b = __float2int_rn(__fadd_rn(__fmul_rn(xy.x, tcos), __fmul_rn(xy.y, tsin))) - rlo;
-                u32 sa = row_sa + (((u32)b << 1) & ~3u);
-                u32 val = one << (((u32)b & 1u) << 4);
-                asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(sa), "r"(val) : "memory");
+#pragma unroll 4
+            for (int i = 0; i < 16; i += PPW) {
+                const float4 xy = stage[i + sub];
+                vote(xy.x, xy.y, true);
+                vote(xy.z, xy.w, true);
             }
         } else {
-            for (int j = 0; j < cntw; j += PPW) {
-                float2 xy = stage[(j + sub) & 31];
-                int b = __float2int_rn(__fadd_rn(__fmul_rn(xy.x, tcos), __fmul_rn(xy.y, tsin))) - rlo;
-                u32 sa = row_sa + (((u32)b << 1) & ~3u);
-                u32 val = (j + sub < cntw ? one : 0u) << (((u32)b & 1u) << 4);
-                asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(sa), "r"(val) : "memory");
+            for (int i = 0; i < 16; i += PPW) {
+                const float4 xy = stage[i + sub];
+                vote(xy.x, xy.y, 2 * (i + sub) < cntw);
+                vote(xy.z, xy.w, 2 * (i + sub) + 1 < cntw);
             }
         }
     }
