@@ -3,13 +3,16 @@
 // Design (B200): the accumulator row of one angle only has support on the rho interval the image
 // rectangle projects to (<= image diagonal + a few bins, although cv2 allocates 2(w+h)+1 bins).  A CTA
 // owns one frame and a stripe of A angles (A-2 output rows + 1 halo row each side for the peak
-// test) and keeps that support as packed u16 counters in shared memory (A x stride x 2 B).  Voting
-// maps LANES to ANGLES, so a warp-wide shared atomic never has an intra-warp address collision, and
-// a pixel's coordinates are warp-uniform (shuffle broadcast).  Each CTA then streams its rows of
-// the int32 accumulator to HBM exactly once with 128-bit stores: zeros outside the support, and
-// inside it one LDS.64 -> four int32 per lane.  The origin of every shared row is shifted by up to
-// 3 bins so that bin 4k of the row lands on a 16-byte boundary of the global row.  Peaks are tested
-// straight from shared memory (packed compare first), so the accumulator is never re-read.
+// test) and keeps that support as packed u16 counters in shared memory (A x stride x 2 B, two angle
+// rows per word, see hist_get).  Voting maps LANES to ANGLES: a pixel's coordinates are warp-uniform
+// (LDS.128 broadcast of two staged pixels), a lane's increment is a constant and its address one
+// multiply-add on the bits of the magic-number-rounded float.  The kernel is bound by the SM's LSU data
+// pipe (shared atomics + gathers + stores), so the 63 % of the int32 accumulator that lies outside
+// the supports is written by the copy engine instead: bulk stores (cp.async.bulk, UBLKCP) from a
+// zeroed shared buffer.  Inside the support each lane gathers four bins of its row and stores 16
+// aligned bytes (the origin of every shared row is shifted by up to 3 bins so that bin 4k lands on a
+// 16-byte boundary of the global row).  Peaks are tested straight from shared memory, so the
+// accumulator is never re-read.
 #include "le_common.cuh"
 #include <vector>
 #include <stdlib.h>
@@ -84,22 +87,31 @@ int le_hough_upload_trig(le_ctx *ctx, int kind, int h, int w, double rho, double
 }
 
 #define HV_THREADS 1024
+#define HV_ZERO_WORDS 1024
 
-static __device__ __forceinline__ int hist_get(const u32 *row, int b, int stride)
+// Shared histogram of a stripe: u16 counters, two ANGLE ROWS per 32-bit word, bin-major:
+//     bin b (relative to the row's origin) of local row a  ->  half (a & 1) of hist[b * (A/2) + (a >> 1)].
+// A vote instruction has lane = angle row, so its increment (1 or 0x10000) is a per-lane constant and its
+// address is ONE multiply-add on the rounded float's bits -- no parity extraction, no shifts.  The two rows
+// of a word never carry into each other (a bin holds at most a few thousand votes).  Lanes of one
+// instruction spread over banks (b % (64/A)) * (A/2) + (a >> 1): about two wavefronts per shared atomic.
+template <int A>
+static __device__ __forceinline__ int hist_get(const u32 *hist, int a, int b, int stride)
 {
-    return (b >= 0 && b < stride) ? (int)((row[b >> 1] >> ((b & 1) * 16)) & 0xffff) : 0;
+    return (b >= 0 && b < stride) ? (int)((hist[b * (A / 2) + (a >> 1)] >> ((a & 1) * 16)) & 0xffff) : 0;
 }
 
 // A = angles per CTA including the two halo rows; 32 % A == 0.
 template <int A>
-__global__ void __launch_bounds__(HV_THREADS)
+__global__ void __launch_bounds__(HV_THREADS, (A <= 16 ? 2 : 1))
 k_hough_vote(const u32 *__restrict__ queue, int *__restrict__ counters, const float *__restrict__ trig,
              int32_t *__restrict__ accum, u64 *__restrict__ peaks, int peak_cap, int h, int w, int numangle,
              int numrho, int stride, int threshold)
 {
-    extern __shared__ __align__(16) u32 hist[];  // [A][stride/2]
+    extern __shared__ __align__(16) u32 hist[];  // [stride][A/2]
     __shared__ int s_rlo[A];
     __shared__ __align__(16) float2 s_stage[HV_THREADS / 32][32];
+    __shared__ __align__(16) u32 s_zero[HV_ZERO_WORDS];  // source of the bulk zero stores
     const int f = blockIdx.y;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nwarps = HV_THREADS / 32;
@@ -119,6 +131,8 @@ k_hough_vote(const u32 *__restrict__ queue, int *__restrict__ counters, const fl
     {
         uint4 *hz = (uint4 *)hist;
         for (int i = tid; i < A * hw / 4; i += HV_THREADS) hz[i] = make_uint4(0, 0, 0, 0);
+        for (int i = tid; i < HV_ZERO_WORDS; i += HV_THREADS) s_zero[i] = 0;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes -> async-proxy reads
     }
     // shared row origin: rlo shifted down so that bin 0 sits on a 16-byte boundary of the global row
     auto row_origin = [&](int n) -> int {
@@ -142,22 +156,20 @@ k_hough_vote(const u32 *__restrict__ queue, int *__restrict__ counters, const fl
         tsin = trig[numangle + n_mine];
         rlo = row_origin(n_mine);
     }
-    // 32-bit shared address of this lane's row.  Lanes of rows outside [0, numangle) (halo of the first /
-    // last stripe) have cos = sin = 0 and vote into bin 0 of their own scratch row, which nobody reads.
-    const u32 row_sa = (u32)__cvta_generic_to_shared(hist + a * hw);
+    // Lanes of rows outside [0, numangle) (halo of the first / last stripe) have cos = sin = 0 and vote into
+    // bin 0 of their own scratch row, which nobody reads.
     // round-half-even by the magic-number add: bits(v + 1.5 * 2^23) - 0x4B400000 == rint(v) for |v| < 2^22,
-    // the same integer __float2int_rn gives; the row origin is folded into the constant
+    // the same integer __float2int_rn gives.  Byte address of the bin's word = col + (rint(v) - rlo) * 2A:
+    // everything but the float's bits is folded into one per-lane constant.
     const float MAGIC = 12582912.f;
-    // byte address of bin b (two u16 bins per word): row_sa + 2 * (b - rlo) with bit 1 cleared; bit 1 says
-    // which half of the word.  row_sa is a multiple of 8, so it can ride in the multiply-add's constant.
-    const u32 kbase = row_sa - 2u * (u32)(0x4B400000 + rlo);
+    const u32 kaddr = (u32)__cvta_generic_to_shared(hist + (a >> 1)) - (u32)(0x4B400000 + rlo) * (2u * A);
+    const u32 inc = (a & 1) ? 0x10000u : 1u;
     float4 *stage = (float4 *)s_stage[warp];  // two staged pixels (x0, y0, x1, y1) per entry
     const float rw = 1.0f / (float)w;
     auto vote = [&](float x, float y, bool on) {
         const float t = __fadd_rn(__fadd_rn(__fmul_rn(x, tcos), __fmul_rn(y, tsin)), MAGIC);
-        const u32 s2 = (u32)__float_as_int(t) * 2u + kbase;
-        const u32 val = on ? ((s2 & 2u) ? 0x10000u : 1u) : 0u;
-        asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(s2 & ~2u), "r"(val) : "memory");
+        const u32 sa = (u32)__float_as_int(t) * (2u * A) + kaddr;
+        asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(sa), "r"(on ? inc : 0u) : "memory");
     };
     __syncthreads();
     for (int base = warp * 32; base < nedge; base += nwarps * 32) {
@@ -197,64 +209,86 @@ k_hough_vote(const u32 *__restrict__ queue, int *__restrict__ counters, const fl
     // rows to write: accumulator rows n+1 for n in [n_first, n_last); plus pad rows 0 and numangle+1
     const int row_lo = (blockIdx.x == 0) ? -1 : n_first;              // as angle index n (row n+1)
     const int row_hi = (n_last == numangle) ? numangle + 1 : n_last;  // exclusive
-    const u32 kcmp = (0x7fffu - (u32)min(max(threshold, 0), 0x7ffe)) * 0x00010001u;
-    for (int n = row_lo + warp; n < row_hi; n += nwarps) {
-        const int la = n - (n_first - 1);  // local row index
-        const bool real = n >= 0 && n < numangle;
-        const u32 *row = hist + la * hw;
-        int32_t *out = acc_f ? acc_f + (size_t)(n + 1) * rowlen : nullptr;
-        // support of this row in accumulator columns: [c_lo, c_hi), c_lo is 16-byte aligned when real
-        int c_lo = real ? roff + s_rlo[la] : rowlen, c_hi = real ? c_lo + stride : rowlen;
-        if (out) {
-            // zero fill left of the support, right of it, and the pad rows (scalar head/tail, int4 body)
+    // (1) zeros left and right of each row's support, and the pad rows: one warp per row; the 16-byte
+    // aligned body of each span goes out as bulk stores issued by lane 0, the few unaligned ints as STG
+    if (acc_f) {
+        const u32 zero_sa = (u32)__cvta_generic_to_shared(s_zero);
+        bool issued = false;
+        for (int n = row_lo + warp; n < row_hi; n += nwarps) {
+            const int la = n - (n_first - 1);  // local row index
+            const bool real = n >= 0 && n < numangle;
+            int32_t *out = acc_f + (size_t)(n + 1) * rowlen;
+            const int c_lo = real ? roff + s_rlo[la] : rowlen, c_hi = real ? c_lo + stride : rowlen;
             int z0 = 0, z1 = min(max(c_lo, 0), rowlen);
 #pragma unroll 1
             for (int part = 0; part < 2; part++) {
                 if (z1 > z0) {
-                    int head = (int)((4 - ((((size_t)(out + z0)) >> 2) & 3)) & 3);
-                    int a0 = min(z0 + head, z1), a1 = a0 + ((z1 - a0) & ~3);
-                    for (int c = z0 + lane; c < a0; c += 32) out[c] = 0;
-                    for (int c = a0 + lane * 4; c < a1; c += 128) *(int4 *)(out + c) = make_int4(0, 0, 0, 0);
-                    for (int c = a1 + lane; c < z1; c += 32) out[c] = 0;
+                    const int head = (int)((4 - ((((size_t)(out + z0)) >> 2) & 3)) & 3);
+                    const int a0 = min(z0 + head, z1), a1 = a0 + ((z1 - a0) & ~3);
+                    if (z0 + lane < a0) out[z0 + lane] = 0;
+                    if (lane == 0) {
+                        for (int c = a0; c < a1; c += HV_ZERO_WORDS)
+                            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(out + c),
+                                         "r"(zero_sa), "r"(4 * min(HV_ZERO_WORDS, a1 - c))
+                                         : "memory");
+                        issued = true;
+                    }
+                    if (a1 + lane < z1) out[a1 + lane] = 0;
                 }
                 z0 = min(max(c_hi, 0), rowlen);
                 z1 = rowlen;
             }
         }
-        if (!real) continue;
-        // support: 4 bins per lane per step (one LDS.64), aligned int4 store when fully inside the row
-        for (int b0 = lane * 4; b0 < stride; b0 += 128) {
-            const uint2 wv = *(const uint2 *)(row + (b0 >> 1));
-            const int c = c_lo + b0;
-            if (out) {
-                if (c >= 0 && c + 3 < rowlen)
-                    *(int4 *)(out + c) = make_int4(wv.x & 0xffff, wv.x >> 16, wv.y & 0xffff, wv.y >> 16);
-                else {
-                    int v[4] = {(int)(wv.x & 0xffff), (int)(wv.x >> 16), (int)(wv.y & 0xffff), (int)(wv.y >> 16)};
+        if (issued) asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+    // (2) the supports: lane = (row a, slot sub); a warp step covers 4 * PPW bins of every row of the
+    // stripe -- each lane gathers four consecutive bins of ITS row and stores 16 bytes to ITS global row
+    // (the row origin was shifted so that this store is aligned); peaks are tested from shared memory
+    {
+        const bool out_row = a >= 1 && a <= A - 2 && n_mine < n_last && row_ok;
+        const int c_lo = roff + rlo;
+        int32_t *out = (acc_f && out_row) ? acc_f + (size_t)(n_mine + 1) * rowlen + c_lo : nullptr;
+        const int rlo_up = s_rlo[max(a - 1, 0)], rlo_dn = s_rlo[min(a + 1, A - 1)];
+        const u32 *col = hist + (a >> 1);
+        const int sh = (a & 1) * 16;
+        if (out_row) {
+            for (int b0 = 4 * (warp * PPW + sub); b0 < stride; b0 += 4 * PPW * nwarps) {
+                int g[4], v[4];  // (the slots of a row read the four bins in rotated order: distinct banks)
 #pragma unroll
-                    for (int k = 0; k < 4; k++)
-                        if (c + k >= 0 && c + k < rowlen) out[c + k] = v[k];
+                for (int k = 0; k < 4; k++) g[k] = (int)((col[(b0 + ((k + 2 * sub) & 3)) * (A / 2)] >> sh) & 0xffff);
+#pragma unroll
+                for (int m = 0; m < 4; m++) v[m] = (sub & 1) ? g[(m + 2) & 3] : g[m];
+                const int c = c_lo + b0;
+                if (out) {
+                    if (c >= 0 && c + 3 < rowlen)
+                        *(int4 *)(out + b0) = make_int4(v[0], v[1], v[2], v[3]);
+                    else {
+#pragma unroll
+                        for (int k = 0; k < 4; k++)
+                            if (c + k >= 0 && c + k < rowlen) out[b0 + k] = v[k];
+                    }
                 }
-            }
-            if (((__vmaxu2(wv.x, wv.y) + kcmp) & 0x80008000u) == 0) continue;  // nothing above the threshold
-            int v[4] = {(int)(wv.x & 0xffff), (int)(wv.x >> 16), (int)(wv.y & 0xffff), (int)(wv.y >> 16)};
+                if (max(max(v[0], v[1]), max(v[2], v[3])) <= threshold) continue;  // nothing above the threshold
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const int cc = c + k, b = b0 + k;
-                if (v[k] > threshold && cc >= 1 && cc <= numrho) {
-                    int left = hist_get(row, b - 1, stride), right = hist_get(row, b + 1, stride);
-                    int up = 0, down = 0;
-                    if (n - 1 >= 0) up = hist_get(row - hw, cc - roff - s_rlo[la - 1], stride);
-                    if (n + 1 < numangle) down = hist_get(row + hw, cc - roff - s_rlo[la + 1], stride);
-                    if (v[k] > left && v[k] >= right && v[k] > up && v[k] >= down) {
-                        int pos = atomicAdd(&cnt[LE_C_PEAKS], 1);
-                        u32 idx = (u32)((n + 1) * rowlen + cc);
-                        if (pos < peak_cap) pk[pos] = ((u64)(u32)v[k] << 32) | (u64)(0xffffffffu - idx);
+                for (int k = 0; k < 4; k++) {
+                    const int cc = c + k, b = b0 + k;
+                    if (v[k] > threshold && cc >= 1 && cc <= numrho) {
+                        int left = hist_get<A>(hist, a, b - 1, stride), right = hist_get<A>(hist, a, b + 1, stride);
+                        int up = 0, down = 0;
+                        if (n_mine - 1 >= 0) up = hist_get<A>(hist, a - 1, cc - roff - rlo_up, stride);
+                        if (n_mine + 1 < numangle) down = hist_get<A>(hist, a + 1, cc - roff - rlo_dn, stride);
+                        if (v[k] > left && v[k] >= right && v[k] > up && v[k] >= down) {
+                            int pos = atomicAdd(&cnt[LE_C_PEAKS], 1);
+                            u32 idx = (u32)((n_mine + 1) * rowlen + cc);
+                            if (pos < peak_cap) pk[pos] = ((u64)(u32)v[k] << 32) | (u64)(0xffffffffu - idx);
+                        }
                     }
                 }
             }
         }
     }
+    // the bulk zero stores read s_zero: they must be complete before the CTA (and its shared memory) goes
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 // Order the peaks of each frame by (votes desc, index asc) == key desc, emit (rho, theta).
@@ -354,7 +388,7 @@ extern "C" int le_hough_lines(le_ctx *ctx, const uint8_t *edges, int n, int h, i
     if (rc) return rc;
     k_zero_peaks<<<(n + 255) / 256, 256, 0, st>>>((int *)ctx->counters.p, n);
     LE_LAUNCH_CHECK(ctx);
-    size_t budget = (size_t)ctx->smem_optin - 1024 - sizeof(float2) * HV_THREADS;
+    size_t budget = (size_t)ctx->smem_optin - 1024 - sizeof(float2) * HV_THREADS - 4 * HV_ZERO_WORDS;
     // angles per CTA: the largest stripe whose counters leave room for two resident CTAs per SM (their
     // zero / vote / write phases then overlap); fall back to whatever fits one CTA
     size_t two = budget / 2 - 4096;
