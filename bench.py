@@ -194,11 +194,15 @@ def main():
     bounds = [(i * B // S, (i + 1) * B // S) for i in range(S)]
     na, nr = eng.hough_dims(H, W)
     edges = torch.empty((B, H, W), dtype=torch.uint8, device=dev)
-    lines = torch.empty((B, max_lines, 2), dtype=torch.float32, device=dev)
-    counts = torch.empty((B,), dtype=torch.int32, device=dev)
+    # two result sets: with N > 1 the gather of step i runs beside the kernels of step i + 1
+    lines2 = [torch.empty((B, max_lines, 2), dtype=torch.float32, device=dev) for _ in range(2)]
+    counts2 = [torch.empty((B,), dtype=torch.int32, device=dev) for _ in range(2)]
+    lines, counts = lines2[0], counts2[0]
+    state = {"i": 0, "pending": None, "gathered": None}
     accum = torch.empty((B, na + 2, nr + 2), dtype=torch.int32, device=dev)
 
     def step():
+        lines, counts = lines2[state["i"] & 1], counts2[state["i"] & 1]
         if S == 1:
             eng.front_canny(frames, CANNY_LO, CANNY_HI, blur=True, out=edges)
             eng.hough_lines(None, 1.0, np.pi / 180, HOUGH_THR, out=(lines, None, counts, accum))
@@ -214,8 +218,16 @@ def main():
                 join = torch.cuda.Event()
                 join.record(st)
                 main.wait_event(join)
-        if world > 1:  # gather the per-frame results of the whole job
-            gp.dist.gather_results(counts, lines, B * world)
+        if world > 1:  # gather the per-frame results of the whole job, one step behind
+            if state["pending"] is not None:
+                state["gathered"] = state["pending"].wait()
+            state["pending"] = gp.dist.gather_results(counts, lines, B * world, async_op=True, slot=state["i"] & 1)
+        state["i"] += 1
+
+    def drain():
+        if state["pending"] is not None:
+            state["gathered"] = state["pending"].wait()
+            state["pending"] = None
 
     def barrier():
         torch.cuda.synchronize()
@@ -225,6 +237,7 @@ def main():
 
     for _ in range(max(args.warmup, 3)):
         step()
+    drain()
     barrier()
     for e in engs:
         e.check()
@@ -234,6 +247,7 @@ def main():
     while time.perf_counter() - t_load < 1.0:  # keep the GPU under load while the clock sampler collects
         for _ in range(20):
             step()
+        drain()
         torch.cuda.synchronize()
     for e in engs:
         e.timing(True)
@@ -244,6 +258,7 @@ def main():
     ev0.record()
     for _ in range(args.steps):
         step()
+    drain()  # the last step's gather is inside the timed region
     ev1.record()
     barrier()
     ms = ev0.elapsed_time(ev1)

@@ -18,8 +18,27 @@ def shard_range(total, rank, world):
 _gather_cache = {}
 
 
-def gather_results(counts, payload, total, group=None):
+class PendingGather:
+    """Handle of an asynchronous gather: ``wait()`` makes the current stream wait for the collectives and
+    returns (counts [total], payload [total, max_k, ...])."""
+
+    def __init__(self, works, result):
+        self.works, self.result = works, result
+
+    def wait(self):
+        for w in self.works:
+            w.wait()
+        self.works = []
+        return self.result
+
+
+def gather_results(counts, payload, total, group=None, async_op=False, slot=0):
     """All-gather per-frame ``counts`` [b] and padded ``payload`` [b, max_k, ...] from every rank.
+
+    With ``async_op`` the collectives are only enqueued (they start once the current stream reaches this
+    point and run beside whatever is enqueued next) and a ``PendingGather`` is returned; the inputs must
+    stay untouched until its ``wait()``.  ``slot`` selects one of several cached output buffer sets, so a
+    caller that pipelines steps can keep the previous step's result alive.
 
     Ranks may own different numbers of frames (block sharding of ``total``).  Equal shards (the usual
     case) go through one ``all_gather_into_tensor`` per array into cached output buffers; ragged shards
@@ -28,18 +47,18 @@ def gather_results(counts, payload, total, group=None):
     call with the same shapes)."""
     world = dist.get_world_size(group)
     if world == 1:
-        return counts, payload
+        return PendingGather([], (counts, payload)) if async_op else (counts, payload)
     sizes = [shard_range(total, r, world)[1] - shard_range(total, r, world)[0] for r in range(world)]
     bmax = max(sizes)
     if min(sizes) == bmax and counts.shape[0] == bmax:
-        key = (counts.device, counts.dtype, payload.dtype, tuple(payload.shape), world)
+        key = (counts.device, counts.dtype, payload.dtype, tuple(payload.shape), world, slot)
         bufs = _gather_cache.get(key)
         if bufs is None:
             bufs = (counts.new_empty((world * bmax,)), payload.new_empty((world * bmax,) + tuple(payload.shape[1:])))
             _gather_cache[key] = bufs
-        dist.all_gather_into_tensor(bufs[0], counts.contiguous(), group=group)
-        dist.all_gather_into_tensor(bufs[1], payload.contiguous(), group=group)
-        return bufs
+        w0 = dist.all_gather_into_tensor(bufs[0], counts.contiguous(), group=group, async_op=async_op)
+        w1 = dist.all_gather_into_tensor(bufs[1], payload.contiguous(), group=group, async_op=async_op)
+        return PendingGather([w0, w1], bufs) if async_op else bufs
     pad = bmax - counts.shape[0]
     if pad:
         counts = torch.cat([counts, counts.new_zeros((pad,))])
@@ -50,7 +69,7 @@ def gather_results(counts, payload, total, group=None):
     dist.all_gather(all_payload, payload.contiguous(), group=group)
     counts_out = torch.cat([c[:s] for c, s in zip(all_counts, sizes)])
     payload_out = torch.cat([p[:s] for p, s in zip(all_payload, sizes)])
-    return counts_out, payload_out
+    return PendingGather([], (counts_out, payload_out)) if async_op else (counts_out, payload_out)
 
 
 def canny_hough_sharded(engine, frames_local, total, lo, hi, rho, theta, threshold, blur=True, max_lines=1024,

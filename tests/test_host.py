@@ -40,7 +40,13 @@ def _gather_worker(rank, world, port, total, q):
     for i in range(hi - lo):
         payload[i, :counts[i]] = lo + i
     c, p = gdist.gather_results(counts, payload, total)
-    q.put((rank, c.numpy(), p.numpy()))
+    # pipelined form: two steps in flight with separate output slots, waited one step late
+    h0 = gdist.gather_results(counts, payload, total, async_op=True, slot=0)
+    h1 = gdist.gather_results(counts + 1, payload, total, async_op=True, slot=1)
+    c0, p0 = h0.wait()
+    c1, _ = h1.wait()
+    assert torch.equal(c0, c) and torch.equal(p0, p) and torch.equal(c1, c + 1)
+    q.put((rank, c.numpy().copy(), p.numpy().copy()))
     dist.barrier()
     dist.destroy_process_group()
 
