@@ -28,6 +28,7 @@
 #define FR_NS 4
 #endif
 // FR_NS: stages of 4 rows in the bulk-copy (TMA) ring
+#define FR_LEVELS 4
 #define FR_STAGE 224  // entries of a warp's strong / weak staging list (a row adds at most 120)
 #ifndef FR_MINBLK
 #define FR_MINBLK 24
@@ -112,8 +113,9 @@ struct FrontArgs {
     int rows_per_seg, nstrips, nsegs;
     int *work;    // work-item counter of this launch (zeroed before it)
     int nframes;
-    // the last frames of a big batch are cut into shorter segments so that the final work items are small
-    int tail_frame0, tail_rows_per_seg, tail_nsegs;
+    // guided schedule: the batch is cut into FR_LEVELS groups of frames with shorter and shorter row segments,
+    // so that the work items handed out last are small (level l: frames [lvl_frame0[l], lvl_frame0[l+1]))
+    int lvl_frame0[FR_LEVELS + 1], lvl_rows[FR_LEVELS], lvl_nsegs[FR_LEVELS], lvl_item0[FR_LEVELS + 1];
 };
 
 // Pipeline state of one lane (packed 16-bit pairs: l = pixels 0,1; h = pixels 2,3)
@@ -243,19 +245,19 @@ __global__ void __launch_bounds__(FR_WARPS * 32, FR_MINBLK) k_front_rows(FrontAr
     int lut_frame = -1;
     // Persistent warps: work items (frame, segment, strip) are handed out by an atomic counter, so a warp
     // that drew flat strips simply takes more of them and no SM waits for block launches.
-    const int items_main = A.nstrips * A.nsegs * A.tail_frame0;
-    const int items_all = items_main + A.nstrips * A.tail_nsegs * (A.nframes - A.tail_frame0);
 #pragma unroll 1
     for (;;) {
     int item = 0;
     if (lane == 0) item = atomicAdd(A.work, 1);
     item = __shfl_sync(~0u, item, 0);
-    if (item >= items_all) break;
-    const bool tail = item >= items_main;
-    const int rows_per_seg = tail ? A.tail_rows_per_seg : A.rows_per_seg;
-    const int items_per_frame = A.nstrips * (tail ? A.tail_nsegs : A.nsegs);
-    if (tail) item -= items_main;
-    const int f = item / items_per_frame + (tail ? A.tail_frame0 : 0);
+    if (item >= A.lvl_item0[FR_LEVELS]) break;
+    int lvl = 0;
+#pragma unroll
+    for (int l = 1; l < FR_LEVELS; l++) lvl += item >= A.lvl_item0[l];
+    const int rows_per_seg = A.lvl_rows[lvl];
+    const int items_per_frame = A.nstrips * A.lvl_nsegs[lvl];
+    item -= A.lvl_item0[lvl];
+    const int f = item / items_per_frame + A.lvl_frame0[lvl];
     const int wi = item % items_per_frame;
     if (LUT && f != lut_frame) {  // FR_WARPS == 1: the block is this warp
         __syncwarp();
@@ -712,19 +714,32 @@ static int launch_rows_t(le_ctx *ctx, const u8 *src, u8 *edges, int n, int h, in
     A.nstrips = (w + FR_STRIP - 1) / FR_STRIP;
     // enough warps to fill the machine even for one small frame, long segments for big batches
     long long target_warps = (long long)ctx->sm_count * 32;
-    int rows = 120;
+    int rows = 160;
+    if (const char *e = getenv("LE_FRONT_ROWS")) rows = max(8, atoi(e));  // A/B measurements
     while (rows > 8 && (long long)n * A.nstrips * ((h + rows - 1) / rows) < target_warps) rows /= 2;
     A.rows_per_seg = rows;
     A.nsegs = (h + rows - 1) / rows;
     A.nframes = n;
     A.work = (int *)ctx->counters.p + (size_t)n * LE_C_STRIDE;  // zeroed with the frame counters
-    A.tail_frame0 = n; A.tail_rows_per_seg = rows; A.tail_nsegs = A.nsegs;
-    if (n >= 16 && rows >= 60) {  // about the last tenth of the frames: quarter-length segments
-        A.tail_frame0 = n - (n + 9) / 10;
-        A.tail_rows_per_seg = rows / 4;
-        A.tail_nsegs = (h + A.tail_rows_per_seg - 1) / A.tail_rows_per_seg;
+    // Guided schedule.  A big batch: the first half of the frames in `rows`-row segments, then a quarter
+    // in rows/2, the rest in rows/4 (each segment re-runs 8 warm-up rows, so short segments are only worth
+    // it where they shorten the tail; measured best of 1..4 levels x 90..360 rows).  A small batch: one level.
+    int nlv = (n >= 16 && rows >= 64) ? FR_LEVELS - 1 : 1;
+    if (const char *e = getenv("LE_FRONT_LEVELS")) nlv = max(1, min(FR_LEVELS, atoi(e)));  // A/B measurements
+    long long items = 0;
+    int f0 = 0;
+    for (int l = 0; l < FR_LEVELS; l++) {
+        int f1 = (l >= nlv - 1) ? n : n - (n >> (l + 1));
+        if (l >= nlv) f1 = n;
+        A.lvl_frame0[l] = f0;
+        A.lvl_rows[l] = max(8, rows >> min(l, nlv - 1));
+        A.lvl_nsegs[l] = (h + A.lvl_rows[l] - 1) / A.lvl_rows[l];
+        A.lvl_item0[l] = (int)items;
+        items += (long long)A.nstrips * A.lvl_nsegs[l] * (f1 - f0);
+        f0 = f1;
     }
-    long long items = (long long)A.nstrips * (A.nsegs * (long long)A.tail_frame0 + A.tail_nsegs * (long long)(n - A.tail_frame0));
+    A.lvl_frame0[FR_LEVELS] = n;
+    A.lvl_item0[FR_LEVELS] = (int)items;
     int per_sm = FR_MINBLK;
     if (const char *e = getenv("LE_FRONT_BLOCKS_PER_SM")) per_sm = max(1, min(FR_MINBLK, atoi(e)));  // A/B measurements
     dim3 grid((unsigned)min(items, (long long)ctx->sm_count * per_sm));
