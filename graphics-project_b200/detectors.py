@@ -1,7 +1,8 @@
 """Reference-level detector wrappers with the reference's own signatures.
 
 ``doCanny`` (opencv.py:21-28), ``lsd`` (opencv.py:204-209), ``prob`` (opencv.py:211-219),
-``lineMatrixToPairs`` (util.py:110-113) and ``_getIntersections`` (opencv.py:171-189).  Each wrapper
+``lineMatrixToPairs`` (util.py:110-113), ``_getIntersections`` (opencv.py:171-189) and
+``combineParallelLines`` (util.py:141-159).  Each wrapper
 issues the fused GPU chain instead of one call per cv2 stage, so a BGR frame is read once.
 """
 import numpy as np
@@ -81,3 +82,25 @@ def _getIntersections(lines):
     n = int(count.item())
     pts = out[:n].cpu().numpy()
     return [(float(x), float(y)) for x, y in pts]
+
+
+def combineParallelLines(lines, max_distance=5, max_angle=3):
+    """util.py:141-159 -- greedy merge of nearly parallel, nearby segments (first mergeable pair, restart).
+
+    ``lines``: list of (p1, p2) point pairs (or (2, 2) arrays) as ``lsd`` / ``prob`` return them.  Like the
+    reference, untouched segments come back as the caller's own objects and merged ones as new float64
+    (2, 2) arrays; arithmetic is float64 throughout (the reference computes float32 inputs in float32)."""
+    if len(lines) < 2:
+        return list(lines)
+    arr = np.array([[l[0][0], l[0][1], l[1][0], l[1][1]] for l in lines], dtype=np.float64)
+    eng = default_engine()
+    out, src, counts = eng.combine_parallel_lines(torch.from_numpy(arr)[None], None, max_distance, max_angle)
+    m = int(counts[0].item())
+    out, src = out[0, :m].cpu().numpy(), src[0, :m].cpu().numpy()
+    res = []
+    for k in range(m):
+        if src[k] & 0x40000000:
+            res.append(np.array([[out[k, 0], out[k, 1]], [out[k, 2], out[k, 3]]]))
+        else:
+            res.append(lines[int(src[k])])
+    return res

@@ -7,6 +7,7 @@ Variable-length results come back padded ``[N, max_k, ...]`` together with ``cou
 import ctypes as C
 import math
 
+import numpy as np
 import torch
 
 from . import _native
@@ -221,6 +222,24 @@ class Engine:
         self._ok(lib.le_pair_intersections(self._ctx, _ptr(lines), m, _ptr(out), _ptr(count), max_out,
                                            self._stream()))
         return out, count
+
+
+    def combine_parallel_lines(self, segs, counts=None, max_distance=5, max_angle=3):
+        """Batched combineParallelLines (util.py:141-159): segs [N, max_k, 4] float64 (x1,y1,x2,y2), counts [N]
+        or None.  Returns (segs [N, max_k, 4], src [N, max_k] int32, counts [N] int32); src holds the original
+        index of each surviving slot with bit 30 set when the slot is a merged segment."""
+        segs = segs.to(self.device, torch.float64).contiguous()
+        n, max_k = segs.shape[0], segs.shape[1]
+        if counts is not None:
+            counts = counts.to(self.device, torch.int32).contiguous()
+        out = torch.empty_like(segs)
+        src = torch.empty((n, max_k), dtype=torch.int32, device=self.device)
+        out_counts = torch.empty((n,), dtype=torch.int32, device=self.device)
+        cosd = lambda a: float(np.cos(np.radians(a)))  # noqa: E731  (the reference's own expression)
+        self._ok(lib.le_combine_parallel_lines(self._ctx, _ptr(segs), _ptr(counts) if counts is not None else None, n,
+                                               max_k, float(max_distance), cosd(max_angle), 5.0, cosd(3), _ptr(out),
+                                               _ptr(src), _ptr(out_counts), self._stream()))
+        return out, src, out_counts
 
 
 _default = {}

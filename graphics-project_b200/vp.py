@@ -162,6 +162,33 @@ def classifyEdges(edges, threshold_multiplier=1.2):
     return x_edges, y_edges, z_edges, phi, theta
 
 
+def smoothEdges(x_edges, y_edges, z_edges):
+    """opencv_renewed.py:56-60: combineParallelLines on each of the three classified edge lists -- one batched
+    launch (one CTA per list) instead of three recursive Python scans."""
+    lists = [list(x_edges), list(y_edges), list(z_edges)]
+    max_k = max(len(l) for l in lists)
+    if max_k < 2:
+        return tuple(lists)
+    arr = np.zeros((3, max_k, 4), np.float64)
+    for i, l in enumerate(lists):
+        for k, e in enumerate(l):
+            arr[i, k] = (e[0][0], e[0][1], e[1][0], e[1][1])
+    eng = default_engine()
+    counts = torch.tensor([len(l) for l in lists], dtype=torch.int32)
+    out, src, oc = eng.combine_parallel_lines(torch.from_numpy(arr), counts)
+    out, src, oc = out.cpu().numpy(), src.cpu().numpy(), oc.cpu().numpy()
+    res = []
+    for i, l in enumerate(lists):
+        r = []
+        for k in range(int(oc[i])):
+            if src[i, k] & 0x40000000:
+                r.append(np.array([[out[i, k, 0], out[i, k, 1]], [out[i, k, 2], out[i, k, 3]]]))
+            else:
+                r.append(l[int(src[i, k])])
+        res.append(r)
+    return tuple(res)
+
+
 def get_camera_angles(image, iterations=1000, method="hough", refinement_iterations=500):
     """opencv_fit_color.py:71-93."""
     if method == "hough":

@@ -141,6 +141,20 @@ int le_vp_sphere_hist(le_ctx *ctx, const double *segs, int m, double width, doub
 int le_pair_intersections(le_ctx *ctx, const float *lines, int m, double *out, int32_t *count, int max_out,
                           void *stream);
 
+/* ---- n2  replaces: combineParallelLines(lines, max_distance=5, max_angle=3)   util.py:141-159
+ *      (with combineEdges util.py:115-139, edgeDistance :103-108, getEdgeProjection :27-52; callers
+ *      opencv.py:225 linesToPlanarGraph, graph.py:116 makeGraphFromLines, opencv_renewed.py:56-60 smoothEdges)
+ * Batched: segs float64 [n][max_k][4] (x1,y1,x2,y2), counts int32 [n] or NULL (= max_k each), max_k <= 4096.
+ * Repeats "merge the lexicographically first pair (i<j) whose |cos angle| > cos_max_angle and whose
+ * edgeDistance < max_distance into slot i, delete j" until no pair is left.  As in the reference, the
+ * thresholds passed apply until the first merge and (default_distance, default_cos) = (5, cos 3 deg)
+ * afterwards.  out_segs [n][max_k][4] holds the surviving segments in list order, out_counts [n] their
+ * number, out_src [n][max_k] (optional) the original index of each slot, bit 30 set if it was merged.  */
+int le_combine_parallel_lines(le_ctx *ctx, const double *segs, const int32_t *counts, int n, int max_k,
+                              double max_distance, double cos_max_angle, double default_distance,
+                              double default_cos, double *out_segs, int32_t *out_src, int32_t *out_counts,
+                              void *stream);
+
 #ifdef __cplusplus
 }
 #endif

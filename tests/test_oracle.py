@@ -117,3 +117,16 @@ def test_oracle_vs_live_cv2():
             ref = d.detect(g)[0]
             got = R.lsd(g, refine)[0]
             assert (ref is None and got is None) or np.array_equal(ref, got)
+
+
+@pytest.mark.parametrize("name", ["demo_scarce", "sc_white_2", "old_sc_inf", "sc_cube", "sc_scarce_3_flat"])
+def test_geometry_oracle_vs_reference_merge(name, golden_outputs):
+    """oracle/geometry.py against util.combineParallelLines run by tests/golden/make_golden_merge.py."""
+    import os
+    from oracle import geometry as G
+    gm = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_merge.npz"))
+    for det, tol in (("prob", 1e-9), ("lsd", 1e-3)):
+        out, src, merged = G.combine_parallel_lines(golden_outputs[f"{name}/ref_{det}"].reshape(-1, 4))
+        ref = gm[f"{name}/merge_{det}"]
+        assert out.shape == ref.shape and np.allclose(out, ref, rtol=0, atol=tol)
+        assert len(src) == len(out) and merged.any()
