@@ -18,7 +18,7 @@ def frames(n, h, w, kind, uniq=16):
     return torch.from_numpy(np.stack([u[i % len(u)] for i in range(n)])).cuda()
 
 out = []
-for (n, h, w, kind) in ((256, 1080, 1920, "cubes"), (64, 2160, 3840, "cubes")):
+for (n, h, w, kind) in ((256, 1080, 1920, "cubes"), (1024, 1080, 1920, "cubes"), (128, 2160, 3840, "cubes")):
     t = frames(n, h, w, kind)
     edges = eng.front_canny(t, 5, 150)
     eng.timing(True); eng.timing_read()
@@ -28,7 +28,7 @@ for (n, h, w, kind) in ((256, 1080, 1920, "cubes"), (64, 2160, 3840, "cubes")):
     out.append({"chain": "prob: Canny(5,150)+HoughLinesP(30,50,10)", "n": n, "h": h, "w": w, "ms": round(ms, 3), "fps": round(n / ms * 1e3), "kernels_ms": kt, "segs_mean": float(counts.float().mean())})
     print(json.dumps(out[-1]), flush=True)
     del t, edges
-for (n, h, w, kind) in ((128, 1080, 1920, "voxel"), (128, 1080, 1920, "cave")):
+for (n, h, w, kind) in ((128, 1080, 1920, "voxel"), (512, 1080, 1920, "voxel"), (512, 1080, 1920, "cave")):
     t = frames(n, h, w, kind)
     gray = eng.bgr2gray(t); del t
     eng.timing(True); eng.timing_read()
@@ -56,3 +56,9 @@ d = cv.createLineSegmentDetector(0, scale=.8, sigma_scale=.6, quant=2.0, ang_th=
 t0 = time.perf_counter()
 for _ in range(3): d.detect(g)
 print(json.dumps({"cv2_1thread_lsd_1080p_voxel_ms": round((time.perf_counter() - t0) / 3 * 1e3, 2)}))
+# segment merging: one CTA per list; the reference's recursive Python scan on the same list
+pairs = gp.detectors.lsd(gp.synth.make_frame(3, 400, 600, "cave"))
+segs = torch.from_numpy(np.array([[a[0], a[1], b[0], b[1]] for a, b in pairs], dtype=np.float64))[None].repeat(64, 1, 1).cuda()
+ms = timeit(lambda: eng.combine_parallel_lines(segs))
+_, _, oc = eng.combine_parallel_lines(segs)
+print(json.dumps({"chain": "combineParallelLines", "lists": 64, "segments_in": segs.shape[1], "segments_out": int(oc[0]), "ms_per_64_lists": round(ms, 3)}))
