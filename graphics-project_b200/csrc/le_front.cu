@@ -126,183 +126,6 @@ __global__ void k_apply_lut(const u8 *__restrict__ src, u8 *__restrict__ dst, co
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < npx; i += stride) d[i] = sl[s[i]];
 }
 
-// ------------------------------------------------------------------ fused front + NMS
-#define FT_TW 128
-#define FT_TH 32
-#define FT_THREADS 256
-#define FT_GW (FT_TW + 8)
-#define FT_GH (FT_TH + 8)
-#define FT_PW (FT_TW + 4)
-#define FT_PH (FT_TH + 4)
-#define FT_MW (FT_TW + 2)
-#define FT_MH (FT_TH + 2)
-
-struct FrontSmem {
-    u8 G[FT_GH][FT_GW];       // gray with reflect halo 4 (blur variants only)
-    u16 Hb[FT_GH][FT_PW];     // horizontal blur, Q4
-    u8 P[FT_PH][FT_PW];       // pre-Sobel image at clamped coordinates, halo 2
-    u16 mag[FT_MH][FT_MW];    // |dx|+|dy|, 0 outside the image, halo 1
-    short2 dxy[FT_TH][FT_TW]; // gradient at the tile's own pixels
-    u16 lstrong[FT_TW * FT_TH];
-    u16 lweak[FT_TW * FT_TH];
-    u8 lut[256];
-    int nstrong, nweak, base_strong, base_weak;
-};
-
-static __device__ __forceinline__ u32 gray_of(u32 b, u32 g, u32 r)
-{
-    return (3735u * b + 19235u * g + 9798u * r + 16384u) >> 15;
-}
-
-template <bool BGR>
-static __device__ __forceinline__ u8 load_gray(const u8 *__restrict__ s, int y, int x, int w)
-{
-    if (BGR) {
-        const u8 *p = s + ((size_t)y * w + x) * 3;
-        return (u8)gray_of(p[0], p[1], p[2]);
-    }
-    return s[(size_t)y * w + x];
-}
-
-// Map values written: 0 none, 1 weak candidate, 255 strong.  Queue: strong pixels appended at the
-// front (counter QTAIL), weak candidates at the back (counter WEAK).
-template <bool BGR, bool BLUR, bool LUT>
-__global__ void __launch_bounds__(FT_THREADS)
-k_front_nms(const u8 *__restrict__ src, u8 *__restrict__ map, u32 *__restrict__ queue, int *__restrict__ counters,
-            const u8 *__restrict__ lut, int h, int w, int lo, int hi)
-{
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    FrontSmem &S = *reinterpret_cast<FrontSmem *>(smem_raw);
-    const int f = blockIdx.z;
-    const int tid = threadIdx.x;
-    const size_t npx = (size_t)h * w;
-    const u8 *s = src + (size_t)f * npx * (BGR ? 3 : 1);
-    u8 *m = map + (size_t)f * npx;
-    const int x0 = blockIdx.x * FT_TW, y0 = blockIdx.y * FT_TH;
-
-    if (tid == 0) { S.nstrong = 0; S.nweak = 0; }
-    if (LUT) S.lut[tid] = lut[f * 256 + tid];
-
-    if (BLUR) {
-        // S0: gray tile with REFLECT_101 halo of 4
-        const bool fast = BGR && x0 >= 4 && x0 + FT_TW + 4 <= w && ((w * 3) & 3) == 0;
-        if (fast) {
-            // 4 pixels = 3 aligned words per thread-iteration
-            for (int i = tid; i < FT_GH * (FT_GW / 4); i += FT_THREADS) {
-                int ty = i / (FT_GW / 4), q = i % (FT_GW / 4);
-                int sy = d_reflect101(y0 + ty - 4, h);
-                const u32 *p = (const u32 *)(s + ((size_t)sy * w + (x0 - 4 + q * 4)) * 3);
-                u32 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
-                u32 g0 = gray_of(a & 255, (a >> 8) & 255, (a >> 16) & 255);
-                u32 g1 = gray_of(a >> 24, b & 255, (b >> 8) & 255);
-                u32 g2 = gray_of((b >> 16) & 255, b >> 24, c & 255);
-                u32 g3 = gray_of((c >> 8) & 255, (c >> 16) & 255, c >> 24);
-                *(u32 *)&S.G[ty][q * 4] = g0 | (g1 << 8) | (g2 << 16) | (g3 << 24);
-            }
-        } else {
-            for (int i = tid; i < FT_GH * FT_GW; i += FT_THREADS) {
-                int ty = i / FT_GW, tx = i % FT_GW;
-                S.G[ty][tx] = load_gray<BGR>(s, d_reflect101(y0 + ty - 4, h), d_reflect101(x0 + tx - 4, w), w);
-            }
-        }
-        __syncthreads();
-        // S1: horizontal [1 4 6 4 1] at clamped x
-        for (int i = tid; i < FT_GH * FT_PW; i += FT_THREADS) {
-            int ty = i / FT_PW, tx = i % FT_PW;
-            int c = d_clamp(x0 - 2 + tx, 0, w - 1) - (x0 - 4);
-            const u8 *g = &S.G[ty][c];
-            S.Hb[ty][tx] = g[-2] + 4 * g[-1] + 6 * g[0] + 4 * g[1] + g[2];
-        }
-        __syncthreads();
-        // S2: vertical at clamped y, round, optional LUT
-        for (int i = tid; i < FT_PH * FT_PW; i += FT_THREADS) {
-            int ty = i / FT_PW, tx = i % FT_PW;
-            int c = d_clamp(y0 - 2 + ty, 0, h - 1) - (y0 - 4);
-            u32 v = S.Hb[c - 2][tx] + 4 * S.Hb[c - 1][tx] + 6 * S.Hb[c][tx] + 4 * S.Hb[c + 1][tx] + S.Hb[c + 2][tx];
-            u8 o = (u8)((v + 128) >> 8);
-            S.P[ty][tx] = LUT ? S.lut[o] : o;
-        }
-    } else {
-        __syncthreads();
-        for (int i = tid; i < FT_PH * FT_PW; i += FT_THREADS) {
-            int ty = i / FT_PW, tx = i % FT_PW;
-            u8 o = load_gray<BGR>(s, d_clamp(y0 - 2 + ty, 0, h - 1), d_clamp(x0 - 2 + tx, 0, w - 1), w);
-            S.P[ty][tx] = LUT ? S.lut[o] : o;
-        }
-    }
-    __syncthreads();
-    // S3: Sobel magnitude with halo 1 (0 outside the image); gradient kept for own pixels
-    for (int i = tid; i < FT_MH * FT_MW; i += FT_THREADS) {
-        int ty = i / FT_MW, tx = i % FT_MW;
-        int x = x0 - 1 + tx, y = y0 - 1 + ty;
-        u16 mg = 0;
-        if (x >= 0 && x < w && y >= 0 && y < h) {
-            const u8 *r0 = &S.P[ty][tx], *r1 = &S.P[ty + 1][tx], *r2 = &S.P[ty + 2][tx];
-            int gx = (r0[2] + 2 * r1[2] + r2[2]) - (r0[0] + 2 * r1[0] + r2[0]);
-            int gy = (r2[0] + 2 * r2[1] + r2[2]) - (r0[0] + 2 * r0[1] + r0[2]);
-            mg = (u16)(abs(gx) + abs(gy));
-            if (tx >= 1 && tx <= FT_TW && ty >= 1 && ty <= FT_TH) S.dxy[ty - 1][tx - 1] = make_short2((short)gx, (short)gy);
-        }
-        S.mag[ty][tx] = mg;
-    }
-    __syncthreads();
-    // S4: non-maximum suppression + double threshold, 4 pixels per thread-iteration
-    const bool vec_store = (w & 3) == 0;
-    for (int i = tid; i < FT_TH * (FT_TW / 4); i += FT_THREADS) {
-        int ty = i / (FT_TW / 4), q = i % (FT_TW / 4);
-        int y = y0 + ty;
-        if (y >= h) continue;
-        u32 packed = 0;
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            int tx = q * 4 + k, x = x0 + tx;
-            if (x >= w) break;
-            int mv = S.mag[ty + 1][tx + 1];
-            u32 cls = 0;
-            if (mv > lo) {
-                short2 g = S.dxy[ty][tx];
-                int ax = abs((int)g.x), ay = abs((int)g.y) << 15;
-                int tg22x = ax * 13573;
-                bool keep;
-                if (ay < tg22x) keep = mv > S.mag[ty + 1][tx] && mv >= S.mag[ty + 1][tx + 2];
-                else {
-                    int tg67x = tg22x + (ax << 16);
-                    if (ay > tg67x) keep = mv > S.mag[ty][tx + 1] && mv >= S.mag[ty + 2][tx + 1];
-                    else {
-                        int sg = ((g.x ^ g.y) < 0) ? -1 : 1;
-                        keep = mv > S.mag[ty][tx + 1 - sg] && mv > S.mag[ty + 2][tx + 1 + sg];
-                    }
-                }
-                if (keep) {
-                    if (mv > hi) { cls = 255; S.lstrong[atomicAdd(&S.nstrong, 1)] = (u16)(ty * FT_TW + tx); }
-                    else { cls = 1; S.lweak[atomicAdd(&S.nweak, 1)] = (u16)(ty * FT_TW + tx); }
-                }
-            }
-            if (vec_store) packed |= cls << (8 * k);
-            else m[(size_t)y * w + x] = (u8)cls;
-        }
-        if (vec_store && x0 + q * 4 < w) *(u32 *)(m + (size_t)y * w + x0 + q * 4) = packed;
-    }
-    __syncthreads();
-    // flush the tile's lists to the frame queue
-    int *cnt = counters + f * LE_C_STRIDE;
-    if (tid == 0) {
-        S.base_strong = S.nstrong ? atomicAdd(&cnt[LE_C_QTAIL], S.nstrong) : 0;
-        S.base_weak = S.nweak ? atomicAdd(&cnt[LE_C_WEAK], S.nweak) : 0;
-    }
-    __syncthreads();
-    u32 *q = queue + (size_t)f * npx;
-    // strong + weak never exceed npx in total (each pixel is in at most one list)
-    for (int i = tid; i < S.nstrong; i += FT_THREADS) {
-        int t = S.lstrong[i];
-        q[S.base_strong + i] = (u32)((y0 + t / FT_TW) * w + x0 + t % FT_TW);
-    }
-    for (int i = tid; i < S.nweak; i += FT_THREADS) {
-        int t = S.lweak[i];
-        q[npx - 1 - (S.base_weak + i)] = (u32)((y0 + t / FT_TW) * w + x0 + t % FT_TW);
-    }
-}
-
 // Hysteresis on the sparse queue: one CTA per frame, level-synchronous BFS.  A weak pixel (1)
 // becomes 255 exactly once (atomicOr on its word decides the winner, who appends it).
 // Promoted pixels are appended after the strong seeds; they can overwrite weak-list slots only
@@ -515,24 +338,6 @@ extern "C" int le_minmax_normalize_u8(le_ctx *ctx, const uint8_t *src, uint8_t *
     return LE_OK;
 }
 
-template <bool BGR, bool BLUR, bool LUT>
-static int launch_front_t(le_ctx *ctx, const u8 *src, u8 *edges, int n, int h, int w, int lo, int hi, cudaStream_t st)
-{
-    static bool attr_set = false;
-    if (!attr_set) {
-        LE_CUDA(ctx, cudaFuncSetAttribute(k_front_nms<BGR, BLUR, LUT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)sizeof(FrontSmem)));
-        attr_set = true;
-    }
-    dim3 grid((w + FT_TW - 1) / FT_TW, (h + FT_TH - 1) / FT_TH, n);
-    LE_T0(ctx, LE_K_FRONT, st);
-    k_front_nms<BGR, BLUR, LUT><<<grid, FT_THREADS, sizeof(FrontSmem), st>>>(
-        src, edges, (u32 *)ctx->queue.p, (int *)ctx->counters.p, (const u8 *)ctx->lut.p, h, w, lo, hi);
-    LE_T1(ctx, LE_K_FRONT, st);
-    LE_LAUNCH_CHECK(ctx);
-    return LE_OK;
-}
-
 int le_front_launch(le_ctx *ctx, const u8 *src, int ch, int do_blur, int do_norm, u8 *edges, int n, int h, int w,
                     int lo, int hi, cudaStream_t st)
 {
@@ -568,15 +373,7 @@ int le_front_launch(le_ctx *ctx, const u8 *src, int ch, int do_blur, int do_norm
     }
     k_zero_counters<<<((n + 1) * LE_C_STRIDE + 255) / 256, 256, 0, st>>>((int *)ctx->counters.p, n);
     LE_LAUNCH_CHECK(ctx);
-    if (getenv("LE_FRONT_V1")) {  // previous shared-memory tile kernel, kept for A/B measurements only
-        if (do_norm) rc = launch_front_t<false, false, true>(ctx, in, edges, n, h, w, lo, hi, st);
-        else if (in_ch == 3 && blur) rc = launch_front_t<true, true, false>(ctx, in, edges, n, h, w, lo, hi, st);
-        else if (in_ch == 3) rc = launch_front_t<true, false, false>(ctx, in, edges, n, h, w, lo, hi, st);
-        else if (blur) rc = launch_front_t<false, true, false>(ctx, in, edges, n, h, w, lo, hi, st);
-        else rc = launch_front_t<false, false, false>(ctx, in, edges, n, h, w, lo, hi, st);
-    } else {
-        rc = le_front_rows_launch(ctx, in, in_ch, blur, do_norm, edges, n, h, w, lo, hi, st);
-    }
+    rc = le_front_rows_launch(ctx, in, in_ch, blur, do_norm, edges, n, h, w, lo, hi, st);
     if (rc) return rc;
     LE_T0(ctx, LE_K_HYST, st);
     k_hysteresis<<<n, 1024, 0, st>>>(edges, (u32 *)ctx->queue.p, (int *)ctx->counters.p, h, w);
