@@ -150,7 +150,7 @@ def main():
     ap.add_argument("--batch", type=int, default=BATCH, help="frames per GPU per step")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--streams", type=int, default=int(os.environ.get("LE_BENCH_STREAMS", "2")),
+    ap.add_argument("--streams", type=int, default=int(os.environ.get("LE_BENCH_STREAMS", "1")),
                     help="slices of the batch processed on separate CUDA streams (kernels of different slices overlap)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -281,10 +281,10 @@ def main():
         launches = int(lt.item())
     fps = B * world * args.steps / (ms * 1e-3)
 
-    # ---- roofline of the dominant kernel.  In the timed region the two slices' kernels overlap on the GPU,
-    # so a kernel's event-to-event duration there includes time it shares the SMs with the other slice.
-    # The per-launch duration used for the roofline is therefore taken live from K more steps of the same
-    # workload issued on ONE stream (whole batch per launch, kernels back to back, nothing overlapping).
+    # ---- roofline of the dominant kernel.  With --streams > 1 the slices' kernels overlap on the GPU, so a
+    # kernel's event-to-event duration in the timed region includes time it shares the SMs with the other
+    # slice.  The per-launch duration used for the roofline is therefore taken live from K more steps of the
+    # same workload issued on ONE stream (whole batch per launch, kernels back to back, nothing overlapping).
     front_b, accum_b = algorithmic_bytes(H, W)
     peak, peak_src = hbm_peak()
     kernel_ms_overlapped = {k: v[0] / v[1] for k, v in ktimes.items()}

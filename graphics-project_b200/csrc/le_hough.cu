@@ -101,12 +101,50 @@ static __device__ __forceinline__ int hist_get(const u32 *hist, int a, int b, in
     return (b >= 0 && b < stride) ? (int)((hist[b * (A / 2) + (a >> 1)] >> ((a & 1) * 16)) & 0xffff) : 0;
 }
 
+// Order the peaks of a frame by (votes desc, index asc) == key desc and emit (rho, theta): rank sort (keys
+// are unique, rank = number of larger keys).  Runs in the LAST vote CTA of the frame to finish, with the
+// stripe histogram's shared memory as the key tile.
+static __device__ void sort_frame(const u64 *pk, int total, int peak_cap, int numrho, float rho, float theta,
+                                  float *__restrict__ lines, int32_t *__restrict__ votes, int32_t *__restrict__ counts,
+                                  int max_lines, int f, u64 *tile, int tile_cap)
+{
+    const int n = min(total, peak_cap);
+    if (threadIdx.x == 0) counts[f] = total;
+    const int rowlen = numrho + 2;
+    for (int i0 = 0; i0 < n; i0 += blockDim.x) {
+        int i = i0 + threadIdx.x;
+        u64 key = i < n ? __ldcg(pk + i) : 0;
+        int rank = 0;
+        for (int t0 = 0; t0 < n; t0 += tile_cap) {
+            int tn = min(tile_cap, n - t0);
+            __syncthreads();
+            for (int j = threadIdx.x; j < tn; j += blockDim.x) tile[j] = __ldcg(pk + t0 + j);
+            __syncthreads();
+            if (i < n)
+                for (int j = 0; j < tn; j++) rank += tile[j] > key;
+        }
+        if (i < n && rank < max_lines) {
+            u32 idx = 0xffffffffu - (u32)(key & 0xffffffffu);
+            int v = (int)(key >> 32);
+            int nn = (int)(idx / (u32)rowlen) - 1;
+            int r = (int)idx - (nn + 1) * rowlen - 1;
+            float lr = __fmul_rn(__fsub_rn((float)r, __fmul_rn((float)(numrho - 1), 0.5f)), rho);
+            float lt = __fadd_rn(0.f, __fmul_rn((float)nn, theta));
+            float *o = lines + ((size_t)f * max_lines + rank) * 2;
+            o[0] = lr;
+            o[1] = lt;
+            if (votes) votes[(size_t)f * max_lines + rank] = v;
+        }
+    }
+}
+
 // A = angles per CTA including the two halo rows; 32 % A == 0.
 template <int A>
 __global__ void __launch_bounds__(HV_THREADS, (A <= 16 ? 2 : 1))
 k_hough_vote(const u32 *__restrict__ queue, int *__restrict__ counters, const float *__restrict__ trig,
              int32_t *__restrict__ accum, u64 *__restrict__ peaks, int peak_cap, int h, int w, int numangle,
-             int numrho, int stride, int threshold)
+             int numrho, int stride, int threshold, float rho, float theta, float *__restrict__ lines,
+             int32_t *__restrict__ votes, int32_t *__restrict__ counts, int max_lines)
 {
     extern __shared__ __align__(16) u32 hist[];  // [stride][A/2]
     __shared__ int s_rlo[A];
@@ -287,56 +325,26 @@ k_hough_vote(const u32 *__restrict__ queue, int *__restrict__ counters, const fl
             }
         }
     }
+    // ---- the last CTA of the frame to get here orders the frame's peaks (its histogram is free by then)
+    __shared__ int s_last;
+    __threadfence();  // this thread's peak keys are visible before the CTA signals
+    __syncthreads();
+    if (tid == 0) s_last = atomicAdd(&cnt[LE_C_AUX0], 1) == (int)gridDim.x - 1;
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        const int total = *(volatile int *)&cnt[LE_C_PEAKS];
+        sort_frame(pk, total, peak_cap, numrho, rho, theta, lines, votes, counts, max_lines, f, (u64 *)hist,
+                   A * stride / 4);
+    }
     // the bulk zero stores read s_zero: they must be complete before the CTA (and its shared memory) goes
     asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
-// Order the peaks of each frame by (votes desc, index asc) == key desc, emit (rho, theta).
-// Rank sort: keys are unique, rank = number of larger keys.
-#define HS_THREADS 512
-#define HS_TILE 2048
-__global__ void __launch_bounds__(HS_THREADS)
-k_hough_sort(const u64 *__restrict__ peaks, const int *__restrict__ counters, int peak_cap, int numrho, float rho,
-             float theta, float *__restrict__ lines, int32_t *__restrict__ votes, int32_t *__restrict__ counts,
-             int max_lines)
-{
-    __shared__ u64 tile[HS_TILE];
-    const int f = blockIdx.x;
-    const u64 *pk = peaks + (size_t)f * peak_cap;
-    const int total = counters[f * LE_C_STRIDE + LE_C_PEAKS];
-    const int n = min(total, peak_cap);
-    if (threadIdx.x == 0) counts[f] = total;
-    const int rowlen = numrho + 2;
-    for (int i0 = 0; i0 < n; i0 += HS_THREADS) {
-        int i = i0 + threadIdx.x;
-        u64 key = i < n ? pk[i] : 0;
-        int rank = 0;
-        for (int t0 = 0; t0 < n; t0 += HS_TILE) {
-            int tn = min(HS_TILE, n - t0);
-            __syncthreads();
-            for (int j = threadIdx.x; j < tn; j += HS_THREADS) tile[j] = pk[t0 + j];
-            __syncthreads();
-            if (i < n)
-                for (int j = 0; j < tn; j++) rank += tile[j] > key;
-        }
-        if (i < n && rank < max_lines) {
-            u32 idx = 0xffffffffu - (u32)(key & 0xffffffffu);
-            int v = (int)(key >> 32);
-            int nn = (int)(idx / (u32)rowlen) - 1;
-            int r = (int)idx - (nn + 1) * rowlen - 1;
-            float lr = __fmul_rn(__fsub_rn((float)r, __fmul_rn((float)(numrho - 1), 0.5f)), rho);
-            float lt = __fadd_rn(0.f, __fmul_rn((float)nn, theta));
-            float *o = lines + ((size_t)f * max_lines + rank) * 2;
-            o[0] = lr;
-            o[1] = lt;
-            if (votes) votes[(size_t)f * max_lines + rank] = v;
-        }
-    }
-}
-
 template <int A>
 static int launch_vote(le_ctx *ctx, int n, int h, int w, int numangle, int numrho, int stride, int threshold,
-                       int32_t *accum, int peak_cap, cudaStream_t st)
+                       int32_t *accum, int peak_cap, float rho, float theta, float *lines, int32_t *votes,
+                       int32_t *counts, int max_lines, cudaStream_t st)
 {
     size_t smem = (size_t)A * stride * 2;
     static size_t attr = 0;
@@ -348,7 +356,7 @@ static int launch_vote(le_ctx *ctx, int n, int h, int w, int numangle, int numrh
     LE_T0(ctx, LE_K_VOTE, st);
     k_hough_vote<A><<<dim3(stripes, n), HV_THREADS, smem, st>>>(
         (const u32 *)ctx->queue.p, (int *)ctx->counters.p, (const float *)ctx->trig.p, accum, (u64 *)ctx->peaks.p,
-        peak_cap, h, w, numangle, numrho, stride, threshold);
+        peak_cap, h, w, numangle, numrho, stride, threshold, rho, theta, lines, votes, counts, max_lines);
     LE_T1(ctx, LE_K_VOTE, st);
     LE_LAUNCH_CHECK(ctx);
     return LE_OK;
@@ -357,7 +365,10 @@ static int launch_vote(le_ctx *ctx, int n, int h, int w, int numangle, int numrh
 __global__ void k_zero_peaks(int *counters, int n)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) counters[i * LE_C_STRIDE + LE_C_PEAKS] = 0;
+    if (i < n) {
+        counters[i * LE_C_STRIDE + LE_C_PEAKS] = 0;
+        counters[i * LE_C_STRIDE + LE_C_AUX0] = 0;  // vote CTAs of the frame that have finished
+    }
 }
 
 extern "C" int le_hough_lines(le_ctx *ctx, const uint8_t *edges, int n, int h, int w, double rho, double theta,
@@ -397,16 +408,11 @@ extern "C" int le_hough_lines(le_ctx *ctx, const uint8_t *edges, int n, int h, i
         if ((size_t)cand * stride * 2 <= two) A = cand;
     for (int cand = 32; cand >= 4 && !A; cand >>= 1)
         if ((size_t)cand * stride * 2 <= budget) A = cand;
-    if (A == 32) rc = launch_vote<32>(ctx, n, h, w, numangle, numrho, stride, threshold, accum, peak_cap, st);
-    else if (A == 16) rc = launch_vote<16>(ctx, n, h, w, numangle, numrho, stride, threshold, accum, peak_cap, st);
-    else if (A == 8) rc = launch_vote<8>(ctx, n, h, w, numangle, numrho, stride, threshold, accum, peak_cap, st);
-    else if (A == 4) rc = launch_vote<4>(ctx, n, h, w, numangle, numrho, stride, threshold, accum, peak_cap, st);
+    if (A == 32) rc = launch_vote<32>(ctx, n, h, w, numangle, numrho, stride, threshold, accum, peak_cap, (float)rho, (float)theta, lines, votes, counts, max_lines, st);
+    else if (A == 16) rc = launch_vote<16>(ctx, n, h, w, numangle, numrho, stride, threshold, accum, peak_cap, (float)rho, (float)theta, lines, votes, counts, max_lines, st);
+    else if (A == 8) rc = launch_vote<8>(ctx, n, h, w, numangle, numrho, stride, threshold, accum, peak_cap, (float)rho, (float)theta, lines, votes, counts, max_lines, st);
+    else if (A == 4) rc = launch_vote<4>(ctx, n, h, w, numangle, numrho, stride, threshold, accum, peak_cap, (float)rho, (float)theta, lines, votes, counts, max_lines, st);
     else return le_fail(ctx, LE_ERR_UNSUPPORTED, "image too large for the shared-memory Hough stripes (stride %d)", stride);
     if (rc) return rc;
-    LE_T0(ctx, LE_K_SORT, st);
-    k_hough_sort<<<n, HS_THREADS, 0, st>>>((const u64 *)ctx->peaks.p, (const int *)ctx->counters.p, peak_cap, numrho,
-                                            (float)rho, (float)theta, lines, votes, counts, max_lines);
-    LE_T1(ctx, LE_K_SORT, st);
-    LE_LAUNCH_CHECK(ctx);
     return LE_OK;
 }
