@@ -88,6 +88,7 @@ int le_hough_upload_trig(le_ctx *ctx, int kind, int h, int w, double rho, double
 
 #define HV_THREADS 1024
 #define HV_ZERO_WORDS 1024
+#define HV_CAND_CAP 8192   // per-frame list of peak candidates on stripe-boundary rows
 
 // Shared histogram of a stripe: u16 counters, two ANGLE ROWS per 32-bit word, bin-major:
 //     bin b (relative to the row's origin) of local row a  ->  half (a & 1) of hist[b * (A/2) + (a >> 1)].
@@ -138,13 +139,18 @@ static __device__ void sort_frame(const u64 *pk, int total, int peak_cap, int nu
     }
 }
 
-// A = angles per CTA including the two halo rows; 32 % A == 0.
-template <int A>
+// A = angle rows per CTA, 32 % A == 0.  HALO: the stripe carries one extra row on each side for the peak test
+// (A - 2 output rows).  Without HALO all A rows are output rows -- no pixel is voted twice.  The first and
+// last row of a stripe then miss one neighbour row: their bins that pass every test that can be made from
+// shared memory go to a per-frame candidate list, and the last CTA of the frame to finish (which also orders
+// the peaks) makes the one missing comparison from the global accumulator (L2) -- a few hundred loads per
+// frame.  That needs the accumulator output, so HALO is kept for accum == NULL.
+template <int A, bool HALO>
 __global__ void __launch_bounds__(HV_THREADS, (A <= 16 ? 2 : 1))
 k_hough_vote(const u32 *__restrict__ queue, int *__restrict__ counters, const float *__restrict__ trig,
              int32_t *__restrict__ accum, u64 *__restrict__ peaks, int peak_cap, int h, int w, int numangle,
              int numrho, int stride, int threshold, float rho, float theta, float *__restrict__ lines,
-             int32_t *__restrict__ votes, int32_t *__restrict__ counts, int max_lines)
+             int32_t *__restrict__ votes, int32_t *__restrict__ counts, int max_lines, u64 *__restrict__ cand)
 {
     extern __shared__ __align__(16) u32 hist[];  // [stride][A/2]
     __shared__ int s_rlo[A];
@@ -158,7 +164,9 @@ k_hough_vote(const u32 *__restrict__ queue, int *__restrict__ counters, const fl
     const u32 *q = queue + (size_t)f * npx;
     int *cnt = counters + f * LE_C_STRIDE;
     const int nedge = cnt[LE_C_QTAIL];
-    const int n_first = blockIdx.x * (A - 2);  // first output angle of this stripe
+    constexpr int OUT = HALO ? A - 2 : A;    // output rows per stripe
+    constexpr int A0 = HALO ? 1 : 0;         // local index of the first output row
+    const int n_first = blockIdx.x * OUT;    // first output angle of this stripe
     const int *rlo_g = (const int *)(trig + 2 * numangle);
     const int rowlen = numrho + 2;
     const int roff = (numrho - 1) / 2 + 1;  // accumulator column of r == 0
@@ -179,13 +187,13 @@ k_hough_vote(const u32 *__restrict__ queue, int *__restrict__ counters, const fl
         return rl - (int)(e & 3);
     };
     if (tid < A) {
-        int n = n_first - 1 + tid;
+        int n = n_first - A0 + tid;
         s_rlo[tid] = (n >= 0 && n < numangle) ? row_origin(n) : 0;
     }
     // lane -> (angle row a, pixel sub-slot)
     const int a = lane % A, sub = lane / A;
     constexpr int PPW = 32 / A;  // pixels per warp step
-    const int n_mine = n_first - 1 + a;
+    const int n_mine = n_first - A0 + a;
     const bool row_ok = n_mine >= 0 && n_mine < numangle;
     float tcos = 0.f, tsin = 0.f;
     int rlo = 0;
@@ -243,7 +251,7 @@ k_hough_vote(const u32 *__restrict__ queue, int *__restrict__ counters, const fl
     // ---- write the stripe's accumulator rows + peak test
     int32_t *acc_f = accum ? accum + (size_t)f * asz : nullptr;
     u64 *pk = peaks + (size_t)f * peak_cap;
-    const int n_last = min(n_first + (A - 2), numangle);  // exclusive
+    const int n_last = min(n_first + OUT, numangle);  // exclusive
     // rows to write: accumulator rows n+1 for n in [n_first, n_last); plus pad rows 0 and numangle+1
     const int row_lo = (blockIdx.x == 0) ? -1 : n_first;              // as angle index n (row n+1)
     const int row_hi = (n_last == numangle) ? numangle + 1 : n_last;  // exclusive
@@ -253,7 +261,7 @@ k_hough_vote(const u32 *__restrict__ queue, int *__restrict__ counters, const fl
         const u32 zero_sa = (u32)__cvta_generic_to_shared(s_zero);
         bool issued = false;
         for (int n = row_lo + warp; n < row_hi; n += nwarps) {
-            const int la = n - (n_first - 1);  // local row index
+            const int la = n - (n_first - A0);  // local row index
             const bool real = n >= 0 && n < numangle;
             int32_t *out = acc_f + (size_t)(n + 1) * rowlen;
             const int c_lo = real ? roff + s_rlo[la] : rowlen, c_hi = real ? c_lo + stride : rowlen;
@@ -283,7 +291,9 @@ k_hough_vote(const u32 *__restrict__ queue, int *__restrict__ counters, const fl
     // stripe -- each lane gathers four consecutive bins of ITS row and stores 16 bytes to ITS global row
     // (the row origin was shifted so that this store is aligned); peaks are tested from shared memory
     {
-        const bool out_row = a >= 1 && a <= A - 2 && n_mine < n_last && row_ok;
+        const bool out_row = a >= A0 && a < A0 + OUT && n_mine < n_last && row_ok;
+        // rows whose two neighbour rows are in this stripe (or do not exist) are tested here
+        const bool test_here = (a >= 1 || n_mine == 0) && (a <= A - 2 || n_mine == numangle - 1);
         const int c_lo = roff + rlo;
         int32_t *out = (acc_f && out_row) ? acc_f + (size_t)(n_mine + 1) * rowlen + c_lo : nullptr;
         const int rlo_up = s_rlo[max(a - 1, 0)], rlo_dn = s_rlo[min(a + 1, A - 1)];
@@ -312,27 +322,78 @@ k_hough_vote(const u32 *__restrict__ queue, int *__restrict__ counters, const fl
                     const int cc = c + k, b = b0 + k;
                     if (v[k] > threshold && cc >= 1 && cc <= numrho) {
                         int left = hist_get<A>(hist, a, b - 1, stride), right = hist_get<A>(hist, a, b + 1, stride);
-                        int up = 0, down = 0;
-                        if (n_mine - 1 >= 0) up = hist_get<A>(hist, a - 1, cc - roff - rlo_up, stride);
-                        if (n_mine + 1 < numangle) down = hist_get<A>(hist, a + 1, cc - roff - rlo_dn, stride);
+                        int up = 0, down = 0;  // a neighbour row of another stripe counts as 0 here
+                        if (n_mine - 1 >= 0 && a >= 1) up = hist_get<A>(hist, a - 1, cc - roff - rlo_up, stride);
+                        if (n_mine + 1 < numangle && a <= A - 2) down = hist_get<A>(hist, a + 1, cc - roff - rlo_dn, stride);
                         if (v[k] > left && v[k] >= right && v[k] > up && v[k] >= down) {
-                            int pos = atomicAdd(&cnt[LE_C_PEAKS], 1);
-                            u32 idx = (u32)((n_mine + 1) * rowlen + cc);
-                            if (pos < peak_cap) pk[pos] = ((u64)(u32)v[k] << 32) | (u64)(0xffffffffu - idx);
+                            const u32 idx = (u32)((n_mine + 1) * rowlen + cc);
+                            const u64 key = ((u64)(u32)v[k] << 32) | (u64)(0xffffffffu - idx);
+                            if (test_here) {
+                                int pos = atomicAdd(&cnt[LE_C_PEAKS], 1);
+                                if (pos < peak_cap) pk[pos] = key;
+                            } else {
+                                int pos = atomicAdd(&cnt[LE_C_AUX1], 1);
+                                if (pos < HV_CAND_CAP) cand[(size_t)f * HV_CAND_CAP + pos] = key;
+                            }
                         }
                     }
                 }
             }
         }
     }
-    // ---- the last CTA of the frame to get here orders the frame's peaks (its histogram is free by then)
     __shared__ int s_last;
+    // ---- the last CTA of the frame to get here orders the frame's peaks (its histogram is free by then)
     __threadfence();  // this thread's peak keys are visible before the CTA signals
     __syncthreads();
     if (tid == 0) s_last = atomicAdd(&cnt[LE_C_AUX0], 1) == (int)gridDim.x - 1;
     __syncthreads();
     if (s_last) {
         __threadfence();
+        if (!HALO) {
+            // the one comparison the first / last row of every stripe could not make: its neighbour row in
+            // the adjacent stripe, read from the (now complete) global accumulator; zero outside that row's
+            // support, which is never read (those zeros may still be in flight from the copy engine)
+            auto at = [&](int r, int cc) -> int {
+                const int b = cc - roff - row_origin(r);
+                return (b >= 0 && b < stride) ? __ldcg(acc_f + (size_t)(r + 1) * rowlen + cc) : 0;
+            };
+            auto settle = [&](int r, int cc, int v) {
+                const bool first_row = r % OUT == 0;  // misses the row above; otherwise the row below
+                const bool keep = first_row ? v > at(r - 1, cc) : v >= at(r + 1, cc);
+                if (keep) {
+                    int pos = atomicAdd(&cnt[LE_C_PEAKS], 1);
+                    u32 idx = (u32)((r + 1) * rowlen + cc);
+                    if (pos < peak_cap) pk[pos] = ((u64)(u32)v << 32) | (u64)(0xffffffffu - idx);
+                }
+            };
+            const int ncand = *(volatile int *)&cnt[LE_C_AUX1];
+            if (ncand <= HV_CAND_CAP) {
+                for (int i = tid; i < ncand; i += HV_THREADS) {
+                    const u64 key = __ldcg(cand + (size_t)f * HV_CAND_CAP + i);
+                    const u32 idx = 0xffffffffu - (u32)(key & 0xffffffffu);
+                    const int r = (int)(idx / (u32)rowlen) - 1;
+                    settle(r, (int)(idx - (u32)(r + 1) * rowlen), (int)(key >> 32));
+                }
+            } else {
+                // list overflow (never on real frames): redo the boundary rows from the global accumulator
+                for (int r = 0; r < numangle; r++) {
+                    const bool first_row = r % OUT == 0 && r > 0, last_row = r % OUT == OUT - 1 && r + 1 < numangle;
+                    if (!first_row && !last_row) continue;
+                    const int o_r = row_origin(r);
+                    for (int b = tid; b < stride; b += HV_THREADS) {
+                        const int cc = roff + o_r + b;
+                        if (cc < 1 || cc > numrho) continue;
+                        const int v = at(r, cc);
+                        if (v <= threshold) continue;
+                        const int left = b > 0 ? at(r, cc - 1) : 0, right = b + 1 < stride ? at(r, cc + 1) : 0;
+                        const int other = first_row ? (r + 1 < numangle ? at(r + 1, cc) : 0) : at(r - 1, cc);
+                        if (v > left && v >= right && (first_row ? v >= other : v > other)) settle(r, cc, v);
+                    }
+                }
+            }
+            __threadfence();
+            __syncthreads();
+        }
         const int total = *(volatile int *)&cnt[LE_C_PEAKS];
         sort_frame(pk, total, peak_cap, numrho, rho, theta, lines, votes, counts, max_lines, f, (u64 *)hist,
                    A * stride / 4);
@@ -341,7 +402,7 @@ k_hough_vote(const u32 *__restrict__ queue, int *__restrict__ counters, const fl
     asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
-template <int A>
+template <int A, bool HALO>
 static int launch_vote(le_ctx *ctx, int n, int h, int w, int numangle, int numrho, int stride, int threshold,
                        int32_t *accum, int peak_cap, float rho, float theta, float *lines, int32_t *votes,
                        int32_t *counts, int max_lines, cudaStream_t st)
@@ -349,14 +410,16 @@ static int launch_vote(le_ctx *ctx, int n, int h, int w, int numangle, int numrh
     size_t smem = (size_t)A * stride * 2;
     static size_t attr = 0;
     if (smem > attr) {
-        LE_CUDA(ctx, cudaFuncSetAttribute(k_hough_vote<A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        LE_CUDA(ctx, cudaFuncSetAttribute(k_hough_vote<A, HALO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr = smem;
     }
-    int stripes = (numangle + (A - 2) - 1) / (A - 2);
+    constexpr int OUT = HALO ? A - 2 : A;
+    int stripes = (numangle + OUT - 1) / OUT;
     LE_T0(ctx, LE_K_VOTE, st);
-    k_hough_vote<A><<<dim3(stripes, n), HV_THREADS, smem, st>>>(
+    k_hough_vote<A, HALO><<<dim3(stripes, n), HV_THREADS, smem, st>>>(
         (const u32 *)ctx->queue.p, (int *)ctx->counters.p, (const float *)ctx->trig.p, accum, (u64 *)ctx->peaks.p,
-        peak_cap, h, w, numangle, numrho, stride, threshold, rho, theta, lines, votes, counts, max_lines);
+        peak_cap, h, w, numangle, numrho, stride, threshold, rho, theta, lines, votes, counts, max_lines,
+        (u64 *)ctx->misc.p);
     LE_T1(ctx, LE_K_VOTE, st);
     LE_LAUNCH_CHECK(ctx);
     return LE_OK;
@@ -368,6 +431,7 @@ __global__ void k_zero_peaks(int *counters, int n)
     if (i < n) {
         counters[i * LE_C_STRIDE + LE_C_PEAKS] = 0;
         counters[i * LE_C_STRIDE + LE_C_AUX0] = 0;  // vote CTAs of the frame that have finished
+        counters[i * LE_C_STRIDE + LE_C_AUX1] = 0;  // peak candidates on stripe-boundary rows
     }
 }
 
@@ -397,6 +461,8 @@ extern "C" int le_hough_lines(le_ctx *ctx, const uint8_t *edges, int n, int h, i
     int peak_cap = (int)cap64;
     rc = le_ensure(ctx, &ctx->peaks, sizeof(u64) * (size_t)n * peak_cap);
     if (rc) return rc;
+    rc = le_ensure(ctx, &ctx->misc, sizeof(u64) * (size_t)n * HV_CAND_CAP);
+    if (rc) return rc;
     k_zero_peaks<<<(n + 255) / 256, 256, 0, st>>>((int *)ctx->counters.p, n);
     LE_LAUNCH_CHECK(ctx);
     size_t budget = (size_t)ctx->smem_optin - 1024 - sizeof(float2) * HV_THREADS - 4 * HV_ZERO_WORDS;
@@ -408,10 +474,15 @@ extern "C" int le_hough_lines(le_ctx *ctx, const uint8_t *edges, int n, int h, i
         if ((size_t)cand * stride * 2 <= two) A = cand;
     for (int cand = 32; cand >= 4 && !A; cand >>= 1)
         if ((size_t)cand * stride * 2 <= budget) A = cand;
-    if (A == 32) rc = launch_vote<32>(ctx, n, h, w, numangle, numrho, stride, threshold, accum, peak_cap, (float)rho, (float)theta, lines, votes, counts, max_lines, st);
-    else if (A == 16) rc = launch_vote<16>(ctx, n, h, w, numangle, numrho, stride, threshold, accum, peak_cap, (float)rho, (float)theta, lines, votes, counts, max_lines, st);
-    else if (A == 8) rc = launch_vote<8>(ctx, n, h, w, numangle, numrho, stride, threshold, accum, peak_cap, (float)rho, (float)theta, lines, votes, counts, max_lines, st);
-    else if (A == 4) rc = launch_vote<4>(ctx, n, h, w, numangle, numrho, stride, threshold, accum, peak_cap, (float)rho, (float)theta, lines, votes, counts, max_lines, st);
+    // without halo rows when the accumulator is written (the deferred boundary test reads it back)
+    const bool nohalo = accum != nullptr && A >= 4;
+#define LE_VOTE(AA, HH) launch_vote<AA, HH>(ctx, n, h, w, numangle, numrho, stride, threshold, accum, peak_cap, (float)rho, \
+                                            (float)theta, lines, votes, counts, max_lines, st)
+    if (A == 32) rc = nohalo ? LE_VOTE(32, false) : LE_VOTE(32, true);
+    else if (A == 16) rc = nohalo ? LE_VOTE(16, false) : LE_VOTE(16, true);
+    else if (A == 8) rc = nohalo ? LE_VOTE(8, false) : LE_VOTE(8, true);
+    else if (A == 4) rc = nohalo ? LE_VOTE(4, false) : LE_VOTE(4, true);
+#undef LE_VOTE
     else return le_fail(ctx, LE_ERR_UNSUPPORTED, "image too large for the shared-memory Hough stripes (stride %d)", stride);
     if (rc) return rc;
     return LE_OK;
