@@ -133,7 +133,7 @@ __global__ void k_apply_lut(const u8 *__restrict__ src, u8 *__restrict__ dst, co
 // in the weak list OR a strong seed, and each weak pixel is appended to the front at most once,
 // so front <= nstrong + nweak_promoted and the back holds nweak; a promoted weak pixel occupies
 // two slots.  Capacity is therefore checked and LE_C_OVERFLOW raised if they would collide.
-__global__ void __launch_bounds__(1024) k_hysteresis(u8 *__restrict__ map, u32 *__restrict__ queue,
+__global__ void __launch_bounds__(1024, 2) k_hysteresis(u8 *__restrict__ map, u32 *__restrict__ queue,
                                                      int *__restrict__ counters, int h, int w)
 {
     const int f = blockIdx.x;
@@ -149,42 +149,53 @@ __global__ void __launch_bounds__(1024) k_hysteresis(u8 *__restrict__ map, u32 *
     if (nweak <= 4096 && tail + nweak <= cap) {
         // Few weak candidates (the usual case when hi is low): sweep the WEAK list instead of flooding
         // from every strong pixel.  A weak pixel with a 255 neighbour is promoted; repeat to a fixpoint.
+        // Each thread keeps its (at most four) weak pixels in registers: a sweep is then ONE L2 round trip
+        // (the eight neighbour bytes of every live pixel, issued together) instead of three dependent ones.
         __shared__ int s_changed, s_t2;
+        constexpr int PER = 4;  // nweak <= 4096 and the CTA has 1024 threads
+        u32 pw[PER];
+        bool live[PER];
+#pragma unroll
+        for (int k = 0; k < PER; k++) {
+            const int i = threadIdx.x + k * 1024;
+            live[k] = i < nweak;
+            pw[k] = live[k] ? q[npx - 1 - i] : 0u;
+        }
         if (threadIdx.x == 0) s_t2 = tail;
         for (;;) {
             __syncthreads();
             if (threadIdx.x == 0) s_changed = 0;
             __syncthreads();
-            for (int i = threadIdx.x; i < nweak; i += blockDim.x) {
-                u32 p = q[npx - 1 - i];
-                if (__ldcg(m + p) != 1) continue;
-                int y = (int)(p / (u32)w), x = (int)(p - (u32)y * w);
-                // all 8 neighbour reads are issued together (one L2 round trip, no early exit)
+#pragma unroll
+            for (int k = 0; k < PER; k++) {  // (k >= 1 only with more than 1024 weak pixels)
+                if (!live[k]) continue;
+                const u32 p = pw[k];
+                const int y = (int)(p / (u32)w), x = (int)(p - (u32)y * w);
                 int nb[8];
 #pragma unroll
-                for (int k = 0; k < 8; k++) {
-                    const int dy = (k < 3) ? -1 : (k < 5 ? 0 : 1);
-                    const int dx = (k < 3) ? k - 1 : (k == 3 ? -1 : (k == 4 ? 1 : k - 6));
-                    int yy = y + dy, xx = x + dx;
-                    bool in = yy >= 0 && yy < h && xx >= 0 && xx < w;
-                    nb[k] = in ? (int)__ldcg(m + (size_t)(in ? yy : y) * w + (in ? xx : x)) : 0;
+                for (int j = 0; j < 8; j++) {
+                    const int dy = (j < 3) ? -1 : (j < 5 ? 0 : 1);
+                    const int dx = (j < 3) ? j - 1 : (j == 3 ? -1 : (j == 4 ? 1 : j - 6));
+                    const int yy = y + dy, xx = x + dx;
+                    const bool in = yy >= 0 && yy < h && xx >= 0 && xx < w;
+                    nb[j] = in ? (int)__ldcg(m + (size_t)(in ? yy : y) * w + (in ? xx : x)) : 0;
                 }
                 bool hit = false;
 #pragma unroll
-                for (int k = 0; k < 8; k++) hit |= nb[k] == 255;
+                for (int j = 0; j < 8; j++) hit |= nb[j] == 255;
                 if (hit) {
                     __stcg(m + p, (u8)255);  // single owner: this pixel appears once in the weak list
                     q[atomicAdd(&s_t2, 1)] = p;
                     s_changed = 1;
+                    live[k] = false;
                 }
             }
             __syncthreads();
             if (!s_changed) break;
         }
-        for (int i = threadIdx.x; i < nweak; i += blockDim.x) {
-            u32 p = q[npx - 1 - i];
-            if (__ldcg(m + p) == 1) __stcg(m + p, (u8)0);
-        }
+#pragma unroll
+        for (int k = 0; k < PER; k++)
+            if (live[k]) __stcg(m + pw[k], (u8)0);  // weak candidates that were never reached
         if (threadIdx.x == 0) cnt[LE_C_QTAIL] = s_t2;
         return;
     }
