@@ -250,7 +250,7 @@ def main():
         drain()
         torch.cuda.synchronize()
     for e in engs:
-        e.timing(True)
+        e.timing(os.environ.get("LE_BENCH_EVENTS", "1") != "0")
         e.timing_read()
     launches0 = sum(e.launches for e in engs)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

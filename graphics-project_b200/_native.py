@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, "liblineengine.so")
 LE_OK = 0
 ERRORS = {-1: "LE_ERR_INVALID", -2: "LE_ERR_CUDA", -3: "LE_ERR_NOMEM", -4: "LE_ERR_OVERFLOW", -5: "LE_ERR_UNSUPPORTED"}
 
-_vp, _i, _d, _sz = C.c_void_p, C.c_int, C.c_double, C.c_size_t
+_vp, _i, _d, _sz, _ll = C.c_void_p, C.c_int, C.c_double, C.c_size_t, C.c_longlong
 
 # name -> (restype, argtypes); mirrors include/line_engine.h one to one
 PROTOTYPES = {
@@ -42,6 +42,10 @@ PROTOTYPES = {
     "le_vp_sphere_hist": (_i, [_vp, _vp, _i, _d, _d, _vp, _i, _i, _vp]),
     "le_pair_intersections": (_i, [_vp, _vp, _i, _vp, _vp, _i, _vp]),
     "le_combine_parallel_lines": (_i, [_vp, _vp, _vp, _i, _i, _d, _d, _d, _d, _vp, _vp, _vp, _vp]),
+    "le_f32_bgr2gray": (_i, [_vp, _vp, _ll, _ll, _ll, _ll, _vp, _i, _i, _i, _vp]),
+    "le_f32_gauss5": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
+    "le_f32_minmax_normalize": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "le_f32_front_canny": (_i, [_vp, _vp, _ll, _ll, _ll, _ll, _vp, _i, _i, _i, _d, _d, _vp]),
 }
 
 

@@ -51,6 +51,11 @@ def _dev(a):
     return eng, torch.from_numpy(np.ascontiguousarray(a)).to(eng.device, non_blocking=False)
 
 
+def _is_f32(img, channels):
+    return (isinstance(img, np.ndarray) and img.dtype == np.float32 and
+            ((channels == 1 and img.ndim == 2) or (channels == 3 and img.ndim == 3 and img.shape[2] == 3)))
+
+
 def _check_u8(img, channels, what):
     if not isinstance(img, np.ndarray):
         raise _err(f"{what}: expected a numpy array")
@@ -67,6 +72,9 @@ def cvtColor(src, code, dst=None, dstCn=0):
     """cv.cvtColor(image, cv.COLOR_BGR2GRAY) -- opencv.py:22,205,213."""
     if code != COLOR_BGR2GRAY:
         raise _err(f"cvtColor: only COLOR_BGR2GRAY is on the hot path (code {code})")
+    if _is_f32(src, 3):  # the simulator's frame-buffer image (opencv.py:101-113), any strides
+        eng = default_engine()
+        return eng.f32_bgr2gray(eng.upload_f32_view(src))[0].cpu().numpy()
     _check_u8(src, 3, "cvtColor")
     eng, t = _dev(src)
     return eng.bgr2gray(t[None])[0].cpu().numpy()
@@ -76,6 +84,9 @@ def GaussianBlur(src, ksize, sigmaX, dst=None, sigmaY=0, borderType=4):
     """cv.GaussianBlur(gray, (5,5), 0) -- opencv.py:25; opencv_fit_color.py:77."""
     if tuple(ksize) != (5, 5) or sigmaX != 0 or sigmaY != 0 or borderType != 4:
         raise _err("GaussianBlur: only ksize (5,5), sigma 0, BORDER_REFLECT_101 is on the hot path")
+    if _is_f32(src, 1):
+        eng, t = _dev(src)
+        return eng.f32_gauss5(t[None])[0].cpu().numpy()
     _check_u8(src, 1, "GaussianBlur")
     eng, t = _dev(src)
     return eng.gauss5(t[None])[0].cpu().numpy()
@@ -84,7 +95,10 @@ def GaussianBlur(src, ksize, sigmaX, dst=None, sigmaY=0, borderType=4):
 def normalize(src, dst, alpha=1.0, beta=0.0, norm_type=4, dtype=-1, mask=None):
     """cv.normalize(blurred, None, 0, 255, cv.NORM_MINMAX) -- opencv.py:26."""
     if (alpha, beta, norm_type) != (0, 255, NORM_MINMAX) or mask is not None or dtype not in (-1, 0):
-        raise _err("normalize: only (alpha=0, beta=255, NORM_MINMAX) on uint8 is on the hot path")
+        raise _err("normalize: only (alpha=0, beta=255, NORM_MINMAX) on uint8 / float32 is on the hot path")
+    if _is_f32(src, 1) and dtype == -1:  # float32 in, float32 out; doCanny then truncates with astype(np.uint8)
+        eng, t = _dev(src)
+        return eng.f32_normalize_minmax(t[None])[0].cpu().numpy()
     _check_u8(src, 1, "normalize")
     eng, t = _dev(src)
     return eng.normalize_minmax(t[None])[0].cpu().numpy()

@@ -1,6 +1,7 @@
 """Reference-level detector wrappers with the reference's own signatures.
 
-``doCanny`` (opencv.py:21-28), ``lsd`` (opencv.py:204-209), ``prob`` (opencv.py:211-219),
+``doCanny`` (opencv.py:21-28; uint8 images and the simulator's float32 frame-buffer view,
+``_fboToImage`` opencv.py:101-108), ``lsd`` (opencv.py:204-209), ``prob`` (opencv.py:211-219),
 ``lineMatrixToPairs`` (util.py:110-113), ``_getIntersections`` (opencv.py:171-189) and
 ``combineParallelLines`` (util.py:141-159).  Each wrapper
 issues the fused GPU chain instead of one call per cv2 stage, so a BGR frame is read once.
@@ -23,6 +24,14 @@ def lineMatrixToPairs(lines):
     return [(np.array(line[0][0:2]), np.array(line[0][2:4])) for line in lines]
 
 
+def _fboToImage(fbo):
+    """opencv.py:101-108 -- the frame buffer's RGB float32 bytes, bottom-up, as a BGR top-down VIEW.  No pixel
+    is touched here: ``doCanny`` uploads the raw bytes once and the kernels address them through the view's
+    (negative) strides."""
+    raw = np.frombuffer(fbo.read(components=3, dtype="f4"), dtype="f4")
+    return raw.reshape((fbo.height, fbo.width, 3))[::-1, :, ::-1]
+
+
 def _bgr_dev(image):
     cv._check_u8(image, 3, "detector input")
     eng = default_engine()
@@ -33,6 +42,10 @@ def doCanny(image, thresh_soft=None, thresh_hard=None):
     """gray -> GaussianBlur(5,5) -> normalize(0,255,MINMAX) -> Canny(soft, hard); u8 edge map."""
     lo = CANNY_THRESH_SOFT if thresh_soft is None else thresh_soft
     hi = CANNY_THRESH_HARD if thresh_hard is None else thresh_hard
+    if cv._is_f32(image, 3):
+        # the simulator path (postProcessFbo, opencv.py:110-113): float32 frame-buffer view, consumed in place
+        eng = default_engine()
+        return eng.f32_front_canny(eng.upload_f32_view(image), lo, hi)[0].cpu().numpy()
     eng, t = _bgr_dev(image)
     return eng.front_canny(t, lo, hi, blur=True, normalize=True)[0].cpu().numpy()
 

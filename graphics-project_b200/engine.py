@@ -134,6 +134,85 @@ class Engine:
         self._last_edges_shape = (n, h, w)
         return out
 
+    # ------------------------------------------------------------------ n4: float32 frame-buffer ingest
+    @staticmethod
+    def _f32_strided(src):
+        """(device tensor holding the frame memory, element offset of pixel [0,0,0,0], element strides n,y,x,c)
+        for a float32 [N,H,W,3] CUDA tensor (any strides) or a tuple (base, offset, strides) made by
+        ``upload_f32_view`` (numpy views with negative strides, which torch cannot represent)."""
+        if isinstance(src, tuple):
+            return src
+        if not (isinstance(src, torch.Tensor) and src.is_cuda and src.dtype == torch.float32):
+            raise TypeError("expected a CUDA float32 tensor")
+        if src.dim() == 3:
+            src = src[None]
+        if src.dim() != 4 or src.shape[-1] != 3:
+            raise ValueError("expected [N,H,W,3]")
+        return src, 0, tuple(src.stride()), tuple(src.shape[:3])
+
+    def upload_f32_view(self, view):
+        """Upload the memory behind a float32 numpy view [H,W,3] or [N,H,W,3] WITHOUT materialising the view
+        (``_fboToImage`` returns ``raw.reshape(h,w,3)[::-1,:,::-1]``: negative row and channel strides)."""
+        if view.dtype != np.float32:
+            raise TypeError("expected float32")
+        if view.ndim == 3:
+            view = view[None]
+        if view.ndim != 4 or view.shape[-1] != 3:
+            raise ValueError("expected [N,H,W,3]")
+        if any(s % 4 for s in view.strides):
+            view = np.ascontiguousarray(view)
+        lo = hi = 0  # byte extent of the view relative to its first element
+        for n, s in zip(view.shape, view.strides):
+            if s < 0:
+                lo += (n - 1) * s
+            else:
+                hi += (n - 1) * s
+        raw = (C.c_char * (hi - lo + 4)).from_address(view.__array_interface__["data"][0] + lo)
+        base = torch.frombuffer(raw, dtype=torch.float32).to(self.device)  # `view` keeps the memory alive
+        return base, -lo // 4, tuple(s // 4 for s in view.strides), tuple(view.shape[:3])
+
+    def f32_bgr2gray(self, src):
+        base, off, (sn, sy, sx, sc), (n, h, w) = self._f32_strided(src)
+        out = torch.empty((n, h, w), dtype=torch.float32, device=self.device)
+        self._ok(lib.le_f32_bgr2gray(self._ctx, C.c_void_p(base.data_ptr() + 4 * off), sn, sy, sx, sc, _ptr(out),
+                                     n, h, w, self._stream()))
+        return out
+
+    def _f32_plane(self, t):
+        if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float32):
+            raise TypeError("expected a CUDA float32 tensor")
+        if t.dim() == 2:
+            t = t[None]
+        if t.dim() != 3:
+            raise ValueError("expected [N,H,W]")
+        return t.contiguous()
+
+    def f32_gauss5(self, gray):
+        gray = self._f32_plane(gray)
+        n, h, w = gray.shape
+        out = torch.empty_like(gray)
+        self._ok(lib.le_f32_gauss5(self._ctx, _ptr(gray), _ptr(out), n, h, w, self._stream()))
+        return out
+
+    def f32_normalize_minmax(self, src, as_u8=False):
+        """cv.normalize(f32, None, 0, 255, NORM_MINMAX); ``as_u8`` adds the reference's .astype(np.uint8)."""
+        src = self._f32_plane(src)
+        n, h, w = src.shape
+        out = torch.empty((n, h, w), dtype=torch.uint8 if as_u8 else torch.float32, device=self.device)
+        self._ok(lib.le_f32_minmax_normalize(self._ctx, _ptr(src), None if as_u8 else _ptr(out),
+                                             _ptr(out) if as_u8 else None, n, h, w, self._stream()))
+        return out
+
+    def f32_front_canny(self, src, lo, hi, out=None):
+        """float32 BGR -> gray -> blur5 -> normalize -> uint8 -> Canny (doCanny on a frame-buffer image)."""
+        base, off, (sn, sy, sx, sc), (n, h, w) = self._f32_strided(src)
+        if out is None:
+            out = torch.empty((n, h, w), dtype=torch.uint8, device=self.device)
+        self._ok(lib.le_f32_front_canny(self._ctx, C.c_void_p(base.data_ptr() + 4 * off), sn, sy, sx, sc, _ptr(out),
+                                        n, h, w, float(lo), float(hi), self._stream()))
+        self._last_edges_shape = (n, h, w)
+        return out
+
     # ------------------------------------------------------------------ a5
     @staticmethod
     def hough_dims(h, w, rho=1.0, theta=math.pi / 180):

@@ -155,6 +155,23 @@ int le_combine_parallel_lines(le_ctx *ctx, const double *segs, const int32_t *co
                               double default_cos, double *out_segs, int32_t *out_src, int32_t *out_counts,
                               void *stream);
 
+/* ---- n4  float32 frame-buffer ingest.  replaces: the CV_32F calls doCanny (opencv.py:21-28) makes
+ *      when postProcessFbo (opencv.py:110-113) passes it _fboToImage's float32 view (opencv.py:101-108):
+ *      cv.cvtColor(f32 BGR, BGR2GRAY) -> cv.GaussianBlur(f32,(5,5),0) -> cv.normalize(f32,None,0,255,NORM_MINMAX)
+ *      -> .astype(np.uint8) -> cv.Canny.  Arithmetic = cv2's FMA3 kernels operation for operation (le_f32.cu).
+ * src is addressed with ELEMENT strides (frame, row, pixel, channel; any sign), so the reference's flipped view
+ * `raw.reshape(h, w, 3)[::-1, :, ::-1]` of the raw frame-buffer bytes is consumed in place.
+ * le_f32_minmax_normalize writes the float32 result (dst_f32) and/or its uint8 truncation (dst_u8).        */
+int le_f32_bgr2gray(le_ctx *ctx, const float *src, long long stride_n, long long stride_y, long long stride_x,
+                    long long stride_c, float *gray, int n, int h, int w, void *stream);
+int le_f32_gauss5(le_ctx *ctx, const float *src, float *dst, int n, int h, int w, void *stream);
+int le_f32_minmax_normalize(le_ctx *ctx, const float *src, float *dst_f32, uint8_t *dst_u8, int n, int h, int w,
+                            void *stream);
+/* Fused: float32 BGR (strided) -> gray -> blur5 -> min-max normalise -> uint8 -> Canny(lo, hi); also leaves the
+ * per-frame edge lists for le_hough_lines(edges == NULL) like le_front_canny_u8.                            */
+int le_f32_front_canny(le_ctx *ctx, const float *src, long long stride_n, long long stride_y, long long stride_x,
+                       long long stride_c, uint8_t *edges, int n, int h, int w, double lo, double hi, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -19,6 +19,8 @@
  *   or_hough_*       cv.HoughLines           opencv.py:88,118      opencv_fit_color.py:83
  *   or_hough_lines_p cv.HoughLinesP          opencv.py:35,217
  *   or_lsd           cv.createLineSegmentDetector(...).detect  opencv.py:206-207
+ *   or_f32_*         the same cvtColor / GaussianBlur / normalize on float32 frames
+ *                    _fboToImage opencv.py:101-108 -> doCanny opencv.py:21-28
  *
  * Build: gcc -O2 -ffp-contract=off -fPIC -shared (see oracle/Makefile).
  * -ffp-contract=off matters: cv2's scalar paths are unfused f32/f64.
@@ -100,6 +102,71 @@ void or_normalize_minmax(const u8 *src, u8 *dst, long n)
         float v = fmaf((float)src[i], fs, fb);
         long iv = lrintf(v);
         dst[i] = (u8)(iv < 0 ? 0 : (iv > 255 ? 255 : iv));
+    }
+}
+
+/* ------------------------------------------------- float32 frame-buffer ingest
+ * The simulator path: _fboToImage (opencv.py:101-108) hands doCanny (opencv.py:21-28) a float32 BGR
+ * view, so cvtColor / GaussianBlur / normalize run cv2's CV_32F kernels.  Summation orders below are
+ * the ones of cv2 4.13's SIMD (FMA3) dispatch, found by differential testing against the wheel
+ * (tests/test_oracle.py::test_f32_chain_vs_cv2): every variant with another order differs from cv2
+ * in 2-10 % of the pixels.  cv2's scalar tail (last w mod 16 columns of GaussianBlur) uses another
+ * order; the restatement follows the vector order everywhere and is pinned on widths % 16 == 0.
+ * src is addressed with element strides (the reference's view has negative row and channel strides). */
+void or_f32_bgr2gray(const float *src, long sy, long sx, long sc, float *gray, int h, int w)
+{
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++) {
+            const float *p = src + (long)y * sy + (long)x * sx;
+            float b = p[0], g = p[sc], r = p[2 * sc];
+            gray[(size_t)y * w + x] = fmaf(r, 0.299f, fmaf(b, 0.114f, g * 0.587f));
+        }
+}
+
+void or_f32_gauss5(const float *src, float *dst, int h, int w)
+{
+    const float k0 = 0.375f, k1 = 0.25f, k2 = 0.0625f;
+    float *tmp = (float *)malloc(sizeof(float) * (size_t)h * w);
+    for (int y = 0; y < h; y++) {
+        const float *r = src + (size_t)y * w;
+        for (int x = 0; x < w; x++) {
+            float xm2 = r[reflect101(x - 2, w)], xm1 = r[reflect101(x - 1, w)], x0 = r[x];
+            float x1 = r[reflect101(x + 1, w)], x2 = r[reflect101(x + 2, w)];
+            tmp[(size_t)y * w + x] = fmaf(x0, k0, (xm1 + x1) * k1) + (xm2 + x2) * k2;
+        }
+    }
+    for (int y = 0; y < h; y++) {
+        const float *rm2 = tmp + (size_t)reflect101(y - 2, h) * w, *rm1 = tmp + (size_t)reflect101(y - 1, h) * w;
+        const float *r0 = tmp + (size_t)y * w;
+        const float *r1 = tmp + (size_t)reflect101(y + 1, h) * w, *r2 = tmp + (size_t)reflect101(y + 2, h) * w;
+        for (int x = 0; x < w; x++) dst[(size_t)y * w + x] = (r0[x] * k0 + (rm1[x] + r1[x]) * k1) + (rm2[x] + r2[x]) * k2;
+    }
+    free(tmp);
+}
+
+/* normalize(src f32, None, 0, 255, NORM_MINMAX) -> f32 (dst_f32) and the reference's .astype(np.uint8)
+ * truncation (dst_u8); either output may be NULL */
+void or_f32_normalize_minmax(const float *src, float *dst_f32, u8 *dst_u8, long n)
+{
+    float mn = src[0], mx = src[0];
+    for (long i = 1; i < n; i++) {
+        if (src[i] < mn) mn = src[i];
+        if (src[i] > mx) mx = src[i];
+    }
+    double smin = mn, smax = mx;
+    double scale = (255.0 - 0.0) * ((smax - smin) > DBL_EPSILON ? 1.0 / (smax - smin) : 0.0);
+    /* cv::normalize, rtype == CV_32F: the scale is rounded to float BEFORE the shift is formed, and the
+     * product smin*scale is rounded to float too */
+    scale = (double)(float)scale;
+    double shift = (double)(float)0.0 - (double)(float)(smin * scale);
+    float fs = (float)scale, fb = (float)shift;
+    for (long i = 0; i < n; i++) {
+        float v = fmaf(src[i], fs, fb);
+        if (dst_f32) dst_f32[i] = v;
+        if (dst_u8) {
+            int iv = (int)v; /* numpy astype: truncation toward zero */
+            dst_u8[i] = (u8)(iv < 0 ? 0 : (iv > 255 ? 255 : iv));
+        }
     }
 }
 

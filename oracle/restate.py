@@ -62,6 +62,44 @@ def normalize_minmax(src):
     return out
 
 
+def _f32(a):
+    a = np.ascontiguousarray(a)
+    assert a.dtype == np.float32
+    return a
+
+
+def f32_bgr2gray(view):
+    """float32 BGR (H,W,3), any strides (the reference's _fboToImage view has negative ones) -> f32 gray."""
+    assert view.dtype == np.float32 and view.ndim == 3 and view.shape[2] == 3
+    h, w, _ = view.shape
+    out = np.empty((h, w), np.float32)
+    sy, sx, sc = (s // 4 for s in view.strides)
+    lib().or_f32_bgr2gray(C.c_void_p(view.__array_interface__["data"][0]), C.c_long(sy), C.c_long(sx),
+                          C.c_long(sc), _p(out), C.c_int(h), C.c_int(w))
+    return out
+
+
+def f32_gauss5(gray):
+    gray = _f32(gray)
+    h, w = gray.shape
+    out = np.empty_like(gray)
+    lib().or_f32_gauss5(_p(gray), _p(out), C.c_int(h), C.c_int(w))
+    return out
+
+
+def f32_normalize_minmax(src, as_u8=False):
+    src = _f32(src)
+    out = np.empty(src.shape, np.uint8 if as_u8 else np.float32)
+    lib().or_f32_normalize_minmax(_p(src), None if as_u8 else _p(out), _p(out) if as_u8 else None,
+                                  C.c_long(src.size))
+    return out
+
+
+def f32_do_canny(view, lo=30, hi=50):
+    """doCanny (opencv.py:21-28) on a float32 BGR frame."""
+    return canny(f32_normalize_minmax(f32_gauss5(f32_bgr2gray(view)), as_u8=True), lo, hi)
+
+
 def canny(src, lo, hi, return_nms=False):
     src = _u8(src)
     h, w = src.shape
