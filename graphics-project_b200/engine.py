@@ -320,6 +320,27 @@ class Engine:
                                                _ptr(src), _ptr(out_counts), self._stream()))
         return out, src, out_counts
 
+    def face_quads(self, segs1, segs2, counts1=None, counts2=None, threshold=15, max_out=4096):
+        """Batched quad search of get_faces_from_pairs (opencv_renewed.py:62-112): segs1 [N, max1, 4], segs2
+        [N, max2, 4] float64 (x1,y1,x2,y2), counts [N] or None.  Returns (quads [N, max_out, 4] int32 in the
+        reference's (i,j,k,l) order, faces [N, max_out, 4, 2] float64 oriented, keep [N, max_out] uint8,
+        counts [N] int32 = true number of candidates)."""
+        segs1 = segs1.to(self.device, torch.float64).contiguous()
+        segs2 = segs2.to(self.device, torch.float64).contiguous()
+        n, max1, max2 = segs1.shape[0], segs1.shape[1], segs2.shape[1]
+        if segs2.shape[0] != n:
+            raise ValueError("segs1 and segs2 must hold the same number of problems")
+        c1 = counts1.to(self.device, torch.int32).contiguous() if counts1 is not None else None
+        c2 = counts2.to(self.device, torch.int32).contiguous() if counts2 is not None else None
+        quads = torch.empty((n, max_out, 4), dtype=torch.int32, device=self.device)
+        faces = torch.empty((n, max_out, 4, 2), dtype=torch.float64, device=self.device)
+        keep = torch.empty((n, max_out), dtype=torch.uint8, device=self.device)
+        counts = torch.empty((n,), dtype=torch.int32, device=self.device)
+        self._ok(lib.le_face_quads(self._ctx, _ptr(segs1), _ptr(c1), max1, _ptr(segs2), _ptr(c2), max2, n,
+                                   float(threshold), _ptr(quads), _ptr(faces), _ptr(keep), _ptr(counts), max_out,
+                                   self._stream()))
+        return quads, faces, keep, counts
+
 
 _default = {}
 

@@ -189,6 +189,55 @@ def smoothEdges(x_edges, y_edges, z_edges):
     return tuple(res)
 
 
+def _edge_array(edges, max_k):
+    arr = np.zeros((max_k, 4), np.float64)
+    for k, e in enumerate(edges):
+        arr[k] = (e[0][0], e[0][1], e[1][0], e[1][1])
+    return arr
+
+
+def get_faces_from_pairs_batch(problems, threshold=15):
+    """[(edges1, edges2), ...] -> [faces, ...]: every pair list of one frame (or of many frames) in ONE launch,
+    one CTA per problem (the reference's pipelines call get_faces_from_pairs three times per frame,
+    opencv_renewed.py:176-178)."""
+    problems = [(list(a), list(b)) for a, b in problems]
+    if not problems:
+        return []
+    max1 = max(1, max(len(a) for a, _ in problems))
+    max2 = max(1, max(len(b) for _, b in problems))
+    s1 = np.stack([_edge_array(a, max1) for a, _ in problems])
+    s2 = np.stack([_edge_array(b, max2) for _, b in problems])
+    c1 = torch.tensor([len(a) for a, _ in problems], dtype=torch.int32)
+    c2 = torch.tensor([len(b) for _, b in problems], dtype=torch.int32)
+    eng = default_engine()
+    cap = 4096
+    while True:
+        quads, faces, keep, counts = eng.face_quads(torch.from_numpy(s1), torch.from_numpy(s2), c1, c2, threshold, cap)
+        counts = counts.cpu().numpy()
+        if counts.max() <= cap:
+            break
+        cap = int(counts.max())
+    faces, keep = faces.cpu().numpy(), keep.cpu().numpy()
+    out = []
+    for p in range(len(problems)):
+        fl = []
+        for a in range(int(counts[p])):
+            if not keep[p, a]:
+                continue
+            if np.isnan(faces[p, a]).any():  # lineIntersection returned None: the reference fails here too
+                raise TypeError("'NoneType' object is not subscriptable (parallel neighbouring segments in a face)")
+            fl.append([(float(x), float(y)) for x, y in faces[p, a]])
+        out.append(fl)
+    return out
+
+
+def get_faces_from_pairs(edges1, edges2, threshold=15):
+    """opencv_renewed.py:62-112: quads (e1, e2, e3, e4) with e1, e3 from edges1 and e2, e4 from edges2 whose
+    neighbouring segments lie within ``threshold`` px of each other; corners by lineIntersection; overlapping
+    duplicates removed; list of faces, each a list of four (x, y) tuples, oriented like the reference's."""
+    return get_faces_from_pairs_batch([(edges1, edges2)], threshold)[0]
+
+
 def get_camera_angles(image, iterations=1000, method="hough", refinement_iterations=500):
     """opencv_fit_color.py:71-93."""
     if method == "hough":

@@ -172,6 +172,20 @@ int le_f32_minmax_normalize(le_ctx *ctx, const float *src, float *dst_f32, uint8
 int le_f32_front_canny(le_ctx *ctx, const float *src, long long stride_n, long long stride_y, long long stride_x,
                        long long stride_c, uint8_t *edges, int n, int h, int w, double lo, double hi, void *stream);
 
+/* ---- n3  replaces: get_faces_from_pairs(edges1, edges2, threshold=15)   opencv_renewed.py:62-112
+ *      (with util.py segments_distance :198-209, lineIntersection :54-68, pointInConvexPolygon :162-168,
+ *      faceCircumference :170-171; callers opencv_renewed.py:176-178, 268-270, 278-280, 310-312)
+ * Batched over n problems: segs1 float64 [n][max1][4], segs2 float64 [n][max2][4] (x1,y1,x2,y2), counts1/counts2
+ * int32 [n] or NULL (= max each); max1, max2 <= 1024.  Every quad i<k (edges1), j<l (edges2) whose four
+ * neighbouring segments lie within `threshold` of each other, in the reference's (i, j, k, l) order:
+ * quads int32 [n][max_out][4]; faces float64 [n][max_out][4][2] = the four corner intersections, already
+ * oriented as the reference returns them (a corner of two parallel segments is NaN where the reference raises);
+ * keep uint8 [n][max_out] = 1 if the face survives the reference's duplicate rule; counts int32 [n] = true
+ * number of candidate quads.                                                                              */
+int le_face_quads(le_ctx *ctx, const double *segs1, const int32_t *counts1, int max1, const double *segs2,
+                  const int32_t *counts2, int max2, int n, double threshold, int32_t *quads, double *faces,
+                  uint8_t *keep, int32_t *counts, int max_out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif
