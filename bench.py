@@ -250,7 +250,9 @@ def main():
         drain()
         torch.cuda.synchronize()
     for e in engs:
-        e.timing(os.environ.get("LE_BENCH_EVENTS", "1") != "0")
+        # per-kernel events cost ~22 us per step (8 records): with one stream they are recorded in the separate
+        # roofline pass below instead (same workload, same stream); LE_BENCH_EVENTS=1 puts them back here
+        e.timing(S > 1 or os.environ.get("LE_BENCH_EVENTS", "0") == "1")
         e.timing_read()
     launches0 = sum(e.launches for e in engs)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -474,6 +474,10 @@ extern "C" int le_hough_lines(le_ctx *ctx, const uint8_t *edges, int n, int h, i
         if ((size_t)cand * stride * 2 <= two) A = cand;
     for (int cand = 32; cand >= 4 && !A; cand >>= 1)
         if ((size_t)cand * stride * 2 <= budget) A = cand;
+    if (const char *e = getenv("LE_VOTE_A")) {  // development knob: force the stripe height
+        const int v = atoi(e);
+        if ((v == 4 || v == 8 || v == 16 || v == 32) && (size_t)v * stride * 2 <= budget) A = v;
+    }
     // without halo rows when the accumulator is written (the deferred boundary test reads it back)
     const bool nohalo = accum != nullptr && A >= 4;
 #define LE_VOTE(AA, HH) launch_vote<AA, HH>(ctx, n, h, w, numangle, numrho, stride, threshold, accum, peak_cap, (float)rho, \
