@@ -47,7 +47,7 @@ struct le_ctx {
     le_buf trig;        // float [2][numangle] + int [numangle] (rlo)
     le_buf tmp0, tmp1;  // generic images
     le_buf ppht_accum, ppht_mask, ppht_nz;
-    le_buf lsd0, lsd1, lsd2, lsd3, lsd4, lsd5, lsd6, lsd_tab;
+    le_buf lsd0, lsd1, lsd2, lsd3, lsd4, lsd5, lsd6, lsd7, lsd_tab;
     double lsd_key[4];
     le_buf misc;
     // state shared between le_front_canny_u8 and le_hough_lines

@@ -14,6 +14,7 @@
 // region angle used by the next test); the data parallelism is across frames.
 #include "le_common.cuh"
 #include <vector>
+#include <stdlib.h>
 
 #define LSD_NOTDEF 0xFFFFFFFFu
 #define LSD_USED 0x80000000u
@@ -54,6 +55,73 @@ __global__ void __launch_bounds__(256) k_sepblur_q8(const u8 *__restrict__ src, 
             for (int t = 0; t <= 2 * r; t++) acc += (u32)tp[t] * hb[ty + t][tx];
             d[(size_t)y * w + x] = (u8)((acc + 32768u) >> 16);
         }
+    }
+}
+
+// ------------------------------------------------------------------ 1a': the same blur, word-wide
+// Rows that are multiples of 4 bytes (1080p, 4K, 600x400 ...): the tile is loaded as aligned 32-bit words; the
+// VERTICAL pass runs first on packed pixel pairs (a tap times a byte stays below 2^16 and so does the whole
+// column sum, so one IMAD on (p0 | p1 << 16) serves two pixels), the horizontal pass then reads the u16 column
+// sums back.  Both passes are exact integer sums, so their order does not change the result
+// ((sum_ij t_i t_j p + 32768) >> 16 either way).
+#define SV_TW 128                        // output pixels per tile row (32 words)
+#define SV_TH 32
+#define SV_CW (SV_TW / 4 + 4)            // words per staged row: 8 halo pixels on each side (R <= 8)
+template <int R>
+__global__ void __launch_bounds__(256) k_sepblur_q8_w(const u8 *__restrict__ src, u8 *__restrict__ dst, int h, int w,
+                                                      const int *__restrict__ taps)
+{
+    __shared__ u32 raw[SV_TH + 2 * R][SV_CW];
+    __shared__ __align__(8) u32 vb[SV_TH][SV_CW][2];  // column sums, u16 x 4 per staged word
+    __shared__ int tp[2 * R + 1];
+    const u8 *s = src + (size_t)blockIdx.z * h * w;
+    u8 *d = dst + (size_t)blockIdx.z * h * w;
+    const int x0 = blockIdx.x * SV_TW, y0 = blockIdx.y * SV_TH;
+    if (threadIdx.x < 2 * R + 1) tp[threadIdx.x] = taps[threadIdx.x];
+    const bool interior = x0 >= 8 && x0 + SV_TW + 8 <= w;
+    for (int i = threadIdx.x; i < (SV_TH + 2 * R) * SV_CW; i += 256) {
+        const int ty = i / SV_CW, c = i - ty * SV_CW;
+        const u8 *row = s + (size_t)d_reflect101(y0 + ty - R, h) * w;
+        const int xb = x0 - 8 + 4 * c;
+        u32 v;
+        if (interior) v = *(const u32 *)(row + xb);
+        else {
+            v = 0;
+#pragma unroll
+            for (int k = 0; k < 4; k++) v |= (u32)row[d_reflect101(min(xb + k, 2 * w - 2), w)] << (8 * k);
+        }
+        raw[ty][c] = v;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < SV_TH * SV_CW; i += 256) {
+        const int ty = i / SV_CW, c = i - ty * SV_CW;
+        u32 a01 = 0, a23 = 0;
+#pragma unroll
+        for (int t = 0; t <= 2 * R; t++) {
+            const u32 wd = raw[ty + t][c];
+            a01 += (u32)tp[t] * __byte_perm(wd, 0, 0x4140);
+            a23 += (u32)tp[t] * __byte_perm(wd, 0, 0x4342);
+        }
+        *(uint2 *)vb[ty][c] = make_uint2(a01, a23);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < SV_TH * (SV_TW / 4); i += 256) {
+        const int ty = i / (SV_TW / 4), oc = i - ty * (SV_TW / 4);
+        const int x = x0 + 4 * oc, y = y0 + ty;
+        if (x >= w || y >= h) continue;
+        const u16 *v16 = (const u16 *)vb[ty] + 8 + 4 * oc - R;  // column sum of pixel x - R
+        u32 vv[4 + 2 * R];
+#pragma unroll
+        for (int j = 0; j < 4 + 2 * R; j++) vv[j] = v16[j];
+        u32 out = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            u32 acc = 0;
+#pragma unroll
+            for (int t = 0; t <= 2 * R; t++) acc += (u32)tp[t] * vv[k + t];
+            out |= ((acc + 32768u) >> 16) << (8 * k);
+        }
+        *(u32 *)(d + (size_t)y * w + x) = out;
     }
 }
 
@@ -109,8 +177,7 @@ static __device__ __forceinline__ int grad_s(const u8 *__restrict__ img, int W, 
 }
 
 __global__ void __launch_bounds__(256) k_lsd_grad(const u8 *__restrict__ img, u32 *__restrict__ ang,
-                                                  float2 *__restrict__ cs, int *__restrict__ counters, int H, int W,
-                                                  int s_thr)
+                                                  int *__restrict__ counters, int H, int W, int s_thr)
 {
     const int f = blockIdx.z;
     const u8 *im = img + (size_t)f * H * W;
@@ -126,10 +193,6 @@ __global__ void __launch_bounds__(256) k_lsd_grad(const u8 *__restrict__ img, u3
                 float deg = d_fast_atan2((float)gx, (float)-gy);
                 out = __float_as_uint(deg);
                 smax = s;
-                // cos/sin of the level-line angle exactly as region growing uses them:
-                // cv2 adds cos(float(angle)), sin(float(angle)) to its f32 running sums
-                float af = (float)((double)deg * D2R);
-                cs[(size_t)f * H * W + (size_t)y * W + x] = make_float2((float)cos((double)af), (float)sin((double)af));
             }
         }
         an[(size_t)y * W + x] = out;
@@ -226,23 +289,52 @@ __global__ void __launch_bounds__(32) k_lsd_scatter(const u8 *__restrict__ img, 
     __syncwarp();
     const double coef = lsd_bin_coef(counters, f, n_bins);
     size_t b0 = (size_t)c * LS_CHUNK, b1 = min(npx, b0 + LS_CHUNK);
-    for (size_t i0 = b0; i0 < b1; i0 += 32) {
-        size_t i = i0 + lane;
-        bool def = i < b1 && an[i] != LSD_NOTDEF;
-        int bin = -1 - lane;  // unique negative keys for undefined lanes
-        if (def) {
-            int y = (int)(i / W), x = (int)(i - (size_t)y * W), gx, gy;
-            bin = lsd_bin(grad_s(im, W, x, y, &gx, &gy), coef, n_bins);
+    // 128 pixels per trip: the four angle words of a lane are fetched together (one memory round per trip
+    // instead of four), then ranked 32 at a time in row-major order
+    for (size_t j0 = b0; j0 < b1; j0 += 128) {
+        u32 av[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const size_t i = j0 + 32 * q + lane;
+            av[q] = i < b1 ? __ldg(an + i) : LSD_NOTDEF;
         }
-        u32 peers = __match_any_sync(~0u, bin);
-        if (def) {
-            int rank = __popc(peers & ((1u << lane) - 1));
-            u32 base = off[bin];
-            ord[base + rank] = (u32)i;
-            __syncwarp(peers);
-            if (rank == __popc(peers) - 1) off[bin] = base + rank + 1;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const size_t i = j0 + 32 * q + lane;
+            const bool def = av[q] != LSD_NOTDEF;
+            if (!__any_sync(~0u, def)) continue;
+            int bin = -1 - lane;  // unique negative keys for undefined lanes
+            if (def) {
+                int y = (int)(i / W), x = (int)(i - (size_t)y * W), gx, gy;
+                bin = lsd_bin(grad_s(im, W, x, y, &gx, &gy), coef, n_bins);
+            }
+            u32 peers = __match_any_sync(~0u, bin);
+            if (def) {
+                int rank = __popc(peers & ((1u << lane) - 1));
+                u32 base = off[bin];
+                ord[base + rank] = (u32)i;
+                __syncwarp(peers);
+                if (rank == __popc(peers) - 1) off[bin] = base + rank + 1;
+            }
+            __syncwarp();
         }
-        __syncwarp();
+    }
+}
+
+// cos/sin of the level-line angle exactly as region growing uses them (cv2 adds cos(float(angle)),
+// sin(float(angle)) to its f32 running sums), for the DEFINED pixels only: dense over the ordered list, so the
+// double-precision cos/sin run on full warps instead of on the few defined lanes of an image-order warp
+__global__ void __launch_bounds__(256) k_lsd_cs(const u32 *__restrict__ ang, const u32 *__restrict__ order,
+                                                const int *__restrict__ counters, float2 *__restrict__ cs, size_t npx)
+{
+    const int f = blockIdx.y;
+    const int ndef = counters[f * LE_C_STRIDE + LE_C_AUX0];
+    const u32 *an = ang + (size_t)f * npx, *ord = order + (size_t)f * npx;
+    float2 *c = cs + (size_t)f * npx;
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < ndef; i += gridDim.x * 256) {
+        const u32 p = ord[i];
+        const float af = (float)((double)__uint_as_float(an[p]) * D2R);
+        c[p] = make_float2((float)cos((double)af), (float)sin((double)af));
     }
 }
 
@@ -561,6 +653,277 @@ __global__ void __launch_bounds__(32) k_lsd_grow(const u8 *__restrict__ img, u32
     if (lane == 0) counts[f] = nseg;
 }
 
+// ------------------------------------------------------------------ 4b: speculative region growing
+// K warps per frame grow the next K free seeds of the ordered list AT THE SAME TIME, then warp 0 commits them in
+// seed order, so the result is the sequential one bit for bit:
+//  * nothing is marked USED while growing.  A warp tags the pixels it accepts in a separate plane
+//    (own[p] = round, warp id); plain stores, the last writer wins.
+//  * a pixel tagged in this round by a LOWER id is treated as taken (in seed order that region comes first) and
+//    the id is remembered (relied mask); a pixel tagged by a HIGHER id is taken over.
+//  * commit, in id order: a seed that an earlier region of the round swallowed is void (exactly what the
+//    sequential scan does with a USED seed).  Region w is valid iff none of its pixels is USED by then (all
+//    earlier regions of the round are committed) and no id it relied on turned out void / invalid / refined.  The first region of a round relies on
+//    nobody and is never validated: it IS the sequential next region, so every round makes progress.  At the
+//    first invalid region the commit stops and the next round starts from that seed.
+//  * density refinement (refine >= 1) re-grows with another tolerance: only the first region of a round may do
+//    it (through the sequential code path); any other region that needs it waits to be first.
+#define SG_KMAX 16
+struct SgSlot {
+    u32 seed;     // pixel index of the seed
+    int ord_idx;  // its position in the ordered list
+    int n;        // region size (speculative)
+    u32 relied;   // ids of this round whose tags made this region skip a pixel
+    int serial;   // 1: must be re-run as first of a round (region list overflow)
+    int need_refine;
+    double reg_angle;
+    LsdRect rec;
+};
+
+static __device__ __forceinline__ u32 ld_cg(const u32 *p)
+{
+    u32 v;
+    asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+#define SG_HASH 1024                 // per-warp exact set of the region's pixels (open addressing, shared memory)
+#define SG_HASH_CAP 768              // a larger region waits to be the first of a round
+static __device__ __forceinline__ u32 sg_hash(u32 e) { return (e * 2654435761u) >> 22; }
+
+static __device__ int lsd_grow_spec(volatile u32 *an, volatile u32 *own, const float2 *__restrict__ cs, u32 *reg,
+                                    int reg_cap, u32 *ring, u32 *hset, int W, int H, int sx, int sy, double tol,
+                                    double *reg_angle_out, int lane, u32 round, int wid, u32 *relied_out,
+                                    int *overflow)
+{
+    const u32 tag = ((round << 5) | (u32)wid) + 1u;
+    int n = 0;
+    u32 relied = 0;
+    u32 sv = ld_ca(an + (size_t)sy * W + sx) & ~LSD_USED;
+    double reg_angle = (double)__uint_as_float(sv) * D2R;
+    for (int j = lane; j < SG_HASH; j += 32) hset[j] = 0xFFFFFFFFu;
+    __syncwarp();
+    if (lane == 0) {
+        u32 e = ((u32)sy << 16) | (u32)sx;
+        reg[0] = e;
+        ring[0] = e;
+        own[(size_t)sy * W + sx] = tag;
+        hset[sg_hash(e)] = e;
+    }
+    n = 1;
+    float sumdx = (float)cos(reg_angle), sumdy = (float)sin(reg_angle);
+    __syncwarp();
+    const int ky = lane / 3 - 1, kx = lane % 3 - 1;
+    bool full = false;
+    for (int i = 0; i < n && !full; i++) {
+        u32 pt = (n - i <= LSD_RING) ? ((volatile u32 *)ring)[i & (LSD_RING - 1)] : ((volatile u32 *)reg)[i];
+        int px = (int)(pt & 0xffff), py = (int)(pt >> 16);
+        int xx = px + kx, yy = py + ky;
+        u32 v = LSD_NOTDEF, o = 0;
+        float2 csn = make_float2(0.f, 0.f);
+        if (lane < 9 && xx >= 0 && xx < W && yy >= 0 && yy < H) {
+            v = ld_ca(an + (size_t)yy * W + xx);
+            o = ld_ca(own + (size_t)yy * W + xx);
+            csn = __ldg(cs + (size_t)yy * W + xx);
+        }
+        const bool avail = v != LSD_NOTDEF && !(v & LSD_USED);
+        const bool cur = o != 0 && ((o - 1u) >> 5) == round;
+        const int oid = (int)((o - 1u) & 31u);
+        const bool taken = cur && oid <= wid;  // mine already, or an earlier region of this round
+        relied |= __reduce_or_sync(~0u, (avail && cur && oid < wid) ? (1u << oid) : 0u);
+        u32 candm = __ballot_sync(~0u, avail && !taken) & 0x1ffu;
+        // A tag of a HIGHER id says nothing about this region: that warp may have overwritten this region's own
+        // tag (plain stores race).  The region's exact pixel set (shared-memory hash) settles it.
+        bool mine = false;
+        if (avail && cur && oid > wid) {
+            const u32 e = ((u32)yy << 16) | (u32)xx;
+            for (u32 hx = sg_hash(e);; hx = (hx + 1) & (SG_HASH - 1)) {
+                const u32 t = ((volatile u32 *)hset)[hx];
+                if (t == e) { mine = true; break; }
+                if (t == 0xFFFFFFFFu) break;
+            }
+        }
+        candm &= ~__ballot_sync(~0u, mine);
+        while (candm) {
+            const int k = __ffs(candm) - 1;
+            candm &= candm - 1;
+            u32 vk = __shfl_sync(~0u, v, k);
+            double a = (double)__uint_as_float(vk) * D2R;
+            if (!aligned_to(reg_angle, a, tol)) continue;
+            if (n >= reg_cap || n >= SG_HASH_CAP) { full = true; break; }
+            int ax = px + (k % 3) - 1, ay = py + (k / 3) - 1;
+            if (lane == 0) {
+                u32 e = ((u32)ay << 16) | (u32)ax;
+                own[(size_t)ay * W + ax] = tag;
+                reg[n] = e;
+                ring[n & (LSD_RING - 1)] = e;
+                u32 hx = sg_hash(e);
+                while (hset[hx] != 0xFFFFFFFFu) hx = (hx + 1) & (SG_HASH - 1);
+                hset[hx] = e;
+            }
+            n++;
+            sumdx += __shfl_sync(~0u, csn.x, k);
+            sumdy += __shfl_sync(~0u, csn.y, k);
+            reg_angle = (double)d_fast_atan2(sumdy, sumdx) * D2R;
+        }
+        __syncwarp();
+    }
+    *reg_angle_out = reg_angle;
+    *relied_out = relied;
+    *overflow = full ? 1 : 0;
+    return n;
+}
+
+template <int SG_K>
+__global__ void __launch_bounds__(SG_K * 32) k_lsd_grow_spec(const u8 *__restrict__ img, u32 *__restrict__ ang,
+                                                             u32 *__restrict__ ownbuf,
+                                                             const float2 *__restrict__ csbuf,
+                                                             const u32 *__restrict__ order, u32 *__restrict__ regbuf,
+                                                             const int *__restrict__ counters, LsdParams P,
+                                                             float *__restrict__ segs, double *__restrict__ widths,
+                                                             double *__restrict__ precs, int32_t *__restrict__ counts)
+{
+    const int f = blockIdx.x, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int W = P.W, H = P.H;
+    const size_t npx = (size_t)H * W;
+    const u8 *im = img + (size_t)f * npx;
+    volatile u32 *an = ang + (size_t)f * npx;
+    volatile u32 *own = ownbuf + (size_t)f * npx;
+    const float2 *cs = csbuf + (size_t)f * npx;
+    const u32 *ord = order + (size_t)f * npx;
+    // region lists: warp 0 owns a full-size list (a region can be the whole frame), the others share a second one
+    u32 *reg0 = regbuf + (size_t)f * 2 * npx;
+    const int cap_w = (int)(npx / (SG_K - 1));
+    u32 *reg = wid == 0 ? reg0 : reg0 + npx + (size_t)(wid - 1) * cap_w;
+    const int reg_cap = wid == 0 ? (int)npx : cap_w;
+    const int ndef = counters[f * LE_C_STRIDE + LE_C_AUX0];
+    extern __shared__ __align__(16) u32 s_dyn[];  // [SG_K][LSD_RING] rings, then [SG_K][SG_HASH] pixel sets
+    u32(*s_ring)[LSD_RING] = (u32(*)[LSD_RING])s_dyn;
+    u32(*s_hset)[SG_HASH] = (u32(*)[SG_HASH])(s_dyn + SG_K * LSD_RING);
+    __shared__ SgSlot s_slot[SG_K];
+    __shared__ int s_pos, s_k, s_nseg;
+    if (threadIdx.x == 0) { s_pos = 0; s_nseg = 0; }
+    __syncthreads();
+    for (u32 round = 0;; round++) {
+        // ---- the next SG_K free seeds in order (warp 0)
+        if (wid == 0) {
+            int k = 0, pos = s_pos;
+            while (k < SG_K && pos < ndef) {
+                const int i = pos + lane;
+                u32 pidx = i < ndef ? ord[i] : 0;
+                bool fr = i < ndef && !(ld_cg((const u32 *)an + pidx) & LSD_USED);
+                u32 m = __ballot_sync(~0u, fr);
+                const int rank = __popc(m & ((1u << lane) - 1));
+                if (fr && k + rank < SG_K) {
+                    s_slot[k + rank].seed = pidx;
+                    s_slot[k + rank].ord_idx = i;
+                }
+                const int take = min(__popc(m), SG_K - k);
+                k += take;
+                if (k == SG_K) break;
+                pos += 32;
+            }
+            if (lane == 0) s_k = k;
+        }
+        __syncthreads();
+        const int kc = s_k;
+        if (kc == 0) break;
+        // ---- speculative growth, one warp per seed
+        if (wid < kc) {
+            SgSlot *S = &s_slot[wid];
+            const u32 pidx = S->seed;
+            const int sy = (int)(pidx / (u32)W), sx = (int)(pidx - (u32)sy * W);
+            double reg_angle;
+            u32 relied = 0;
+            int overflow = 0;
+            // the first region of a round is the sequential next region: it marks USED as it grows (any size, no
+            // tags); the others see its pixels as used -- late at worst, which the commit catches
+            int n = wid == 0 ? lsd_grow(an, cs, reg, s_ring[0], W, H, sx, sy, P.prec, &reg_angle, lane)
+                             : lsd_grow_spec(an, own, cs, reg, reg_cap, s_ring[wid], s_hset[wid], W, H, sx, sy, P.prec,
+                                             &reg_angle, lane, round, wid, &relied, &overflow);
+            int need_refine = 0;
+            LsdRect rec;
+            if (!overflow && (unsigned)n >= P.min_reg_size) {
+                lsd_region2rect(im, reg, n, W, reg_angle, P.prec, &rec, lane);
+                if (P.refine > 0) {
+                    double density = (double)n / (dist2d(rec.x1, rec.y1, rec.x2, rec.y2) * rec.width);
+                    need_refine = density < P.density_th;
+                }
+                if (lane == 0) S->rec = rec;
+            }
+            if (lane == 0) {
+                S->n = n;
+                S->relied = relied;
+                S->serial = overflow;
+                S->need_refine = need_refine;
+                S->reg_angle = reg_angle;
+            }
+        }
+        __syncthreads();
+        // ---- ordered commit (warp 0)
+        if (wid == 0) {
+            u32 bad = 0;
+            int w = 0;
+            int nseg = s_nseg;
+            for (; w < kc; w++) {
+                const SgSlot *S = &s_slot[w];
+                if (S->serial && w > 0) break;
+                if (w > 0 && (ld_cg((const u32 *)an + S->seed) & LSD_USED)) {  // swallowed by an earlier region of this round
+                    bad |= 1u << w;
+                    continue;
+                }
+                int n = S->n;
+                const u32 *rg = w == 0 ? reg0 : reg0 + npx + (size_t)(w - 1) * cap_w;
+                if (w > 0) {
+                    if (bad == ~0u || (S->relied & bad)) break;
+                    if (S->need_refine) break;
+                    // every pixel must still be free: all earlier regions of the round are committed by now
+                    bool ok = true;
+                    for (int i = lane; i < n; i += 32) {
+                        u32 pt = ld_cg(rg + i);
+                        size_t p = (size_t)(pt >> 16) * W + (pt & 0xffff);
+                        ok = ok && !(ld_cg((const u32 *)an + p) & LSD_USED);
+                    }
+                    if (!__all_sync(~0u, ok)) break;
+                }
+                if (w > 0) {
+                    for (int i = lane; i < n; i += 32) {
+                        u32 pt = ld_cg(rg + i);
+                        size_t p = (size_t)(pt >> 16) * W + (pt & 0xffff);
+                        an[p] = ld_cg((const u32 *)an + p) | LSD_USED;
+                    }
+                }
+                __syncwarp();
+                if ((unsigned)n < P.min_reg_size) continue;
+                LsdRect rec = S->rec;
+                double reg_angle = S->reg_angle;
+                if (S->need_refine) {  // only the first region of a round: the sequential refinement path
+                    bad = ~0u;  // its pixel set changes: nobody else of this round may commit
+                    if (!lsd_refine(im, an, cs, reg0, s_ring[0], &n, W, H, &reg_angle, P.prec, &rec, P.density_th, lane))
+                        continue;
+                }
+                rec.x1 += 0.5; rec.y1 += 0.5; rec.x2 += 0.5; rec.y2 += 0.5;
+                if (P.scale != 1) {
+                    rec.x1 /= P.scale; rec.y1 /= P.scale; rec.x2 /= P.scale; rec.y2 /= P.scale;
+                    rec.width /= P.scale;
+                }
+                if (lane == 0 && nseg < P.max_segs) {
+                    float *o = segs + ((size_t)f * P.max_segs + nseg) * 4;
+                    o[0] = (float)rec.x1; o[1] = (float)rec.y1; o[2] = (float)rec.x2; o[3] = (float)rec.y2;
+                    if (widths) widths[(size_t)f * P.max_segs + nseg] = rec.width;
+                    if (precs) precs[(size_t)f * P.max_segs + nseg] = P.p;
+                }
+                nseg++;
+            }
+            if (lane == 0) {
+                s_nseg = nseg;
+                s_pos = w < kc ? s_slot[w].ord_idx : s_slot[kc - 1].ord_idx + 1;
+            }
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) counts[f] = s_nseg;
+}
+
 // ------------------------------------------------------------------ host side
 extern "C" int le_lsd_scaled_dims(int h, int w, double scale, int *sh, int *sw)
 {
@@ -641,7 +1004,9 @@ extern "C" int le_lsd(le_ctx *ctx, const uint8_t *gray, int n, int h, int w, int
     if ((rc = le_ensure(ctx, &ctx->lsd1, npx * n))) return rc;                                 // scaled image
     if ((rc = le_ensure(ctx, &ctx->lsd2, sizeof(u32) * npx * n))) return rc;                   // angles
     if ((rc = le_ensure(ctx, &ctx->lsd3, sizeof(u32) * npx * n))) return rc;                   // order
-    if ((rc = le_ensure(ctx, &ctx->lsd4, sizeof(u32) * npx * n))) return rc;                   // region list
+    static const int spec = getenv("LE_LSD_SERIAL") ? 0 : 1;  // development knob: the one-warp-per-frame kernel
+    if ((rc = le_ensure(ctx, &ctx->lsd4, sizeof(u32) * npx * n * (spec ? 2 : 1)))) return rc;  // region lists
+    if (spec && (rc = le_ensure(ctx, &ctx->lsd7, sizeof(u32) * npx * n))) return rc;          // speculative tags
     if ((rc = le_ensure(ctx, &ctx->lsd6, sizeof(float2) * npx * n))) return rc;                // cos/sin of the angles
     if ((rc = le_ensure(ctx, &ctx->lsd5, (sizeof(u16) + sizeof(u32)) * (size_t)nchunk * n_bins * n + 16))) return rc;
     ctx->edge_list_for = nullptr;
@@ -668,8 +1033,15 @@ extern "C" int le_lsd(le_ctx *ctx, const uint8_t *gray, int n, int h, int w, int
             LE_CUDA(ctx, cudaMemcpyAsync(tb + 128 + sizeof(int2) * W, yt.data(), sizeof(int2) * H, cudaMemcpyHostToDevice, st));
             ctx->lsd_key[0] = h; ctx->lsd_key[1] = w; ctx->lsd_key[2] = scale; ctx->lsd_key[3] = sigma_scale;
         }
-        k_sepblur_q8<<<dim3((w + SB_TW - 1) / SB_TW, (h + SB_TH - 1) / SB_TH, n), 256, 0, st>>>(
-            gray, (u8 *)ctx->lsd0.p, h, w, (const int *)tb, (int)hh);
+        const bool wordwise = (w & 3) == 0 && (((size_t)gray) & 3) == 0 && (hh == 3 || hh == 5);
+        const dim3 gw((w + SV_TW - 1) / SV_TW, (h + SV_TH - 1) / SV_TH, n);
+        if (wordwise && hh == 3)
+            k_sepblur_q8_w<3><<<gw, 256, 0, st>>>(gray, (u8 *)ctx->lsd0.p, h, w, (const int *)tb);
+        else if (wordwise)
+            k_sepblur_q8_w<5><<<gw, 256, 0, st>>>(gray, (u8 *)ctx->lsd0.p, h, w, (const int *)tb);
+        else
+            k_sepblur_q8<<<dim3((w + SB_TW - 1) / SB_TW, (h + SB_TH - 1) / SB_TH, n), 256, 0, st>>>(
+                gray, (u8 *)ctx->lsd0.p, h, w, (const int *)tb, (int)hh);
         LE_LAUNCH_CHECK(ctx);
         k_resize_exact<<<dim3((W + 31) / 32, (H + 7) / 8, n), 256, 0, st>>>(
             (const u8 *)ctx->lsd0.p, h, w, (u8 *)ctx->lsd1.p, H, W, (const int2 *)(tb + 128),
@@ -693,8 +1065,7 @@ extern "C" int le_lsd(le_ctx *ctx, const uint8_t *gray, int n, int h, int w, int
     int *cnt = (int *)ctx->counters.p;
     k_lsd_zero<<<(n + 255) / 256, 256, 0, st>>>(cnt, n);
     LE_LAUNCH_CHECK(ctx);
-    k_lsd_grad<<<dim3((W + 31) / 32, (H + 7) / 8, n), 256, 0, st>>>(img, (u32 *)ctx->lsd2.p, (float2 *)ctx->lsd6.p, cnt, H, W,
-                                                                   s_thr);
+    k_lsd_grad<<<dim3((W + 31) / 32, (H + 7) / 8, n), 256, 0, st>>>(img, (u32 *)ctx->lsd2.p, cnt, H, W, s_thr);
     LE_LAUNCH_CHECK(ctx);
     u16 *chist = (u16 *)ctx->lsd5.p;
     u32 *coff = (u32 *)((char *)ctx->lsd5.p + sizeof(u16) * (size_t)nchunk * n_bins * n);
@@ -708,11 +1079,34 @@ extern "C" int le_lsd(le_ctx *ctx, const uint8_t *gray, int n, int h, int w, int
     k_lsd_scatter<<<dim3(nchunk, n), 32, sizeof(u32) * n_bins, st>>>(img, (const u32 *)ctx->lsd2.p, cnt, coff,
                                                                      (u32 *)ctx->lsd3.p, H, W, nchunk, n_bins);
     LE_LAUNCH_CHECK(ctx);
+    k_lsd_cs<<<dim3(64, n), 256, 0, st>>>((const u32 *)ctx->lsd2.p, (const u32 *)ctx->lsd3.p, cnt, (float2 *)ctx->lsd6.p, npx);
+    LE_LAUNCH_CHECK(ctx);
     LE_T1(ctx, LE_K_LSD_PREP, st);
     LE_T0(ctx, LE_K_LSD_GROW, st);
-    k_lsd_grow<<<n, 32, 0, st>>>(img, (u32 *)ctx->lsd2.p, (const float2 *)ctx->lsd6.p, (const u32 *)ctx->lsd3.p,
-                                 (u32 *)ctx->lsd4.p, cnt, P, segs,
-                                 width, prec_out, counts);
+    if (spec) {
+        LE_CUDA(ctx, cudaMemsetAsync(ctx->lsd7.p, 0, sizeof(u32) * npx * n, st));
+        // warps per frame: 16 while every frame's CTA is resident at once (2 per SM: registers and the pixel sets'
+        // shared memory), 8 for bigger batches (4 per SM) -- a second wave costs more than the narrower round
+        int K = n <= 2 * ctx->sm_count ? 16 : 8;
+        if (const char *e = getenv("LE_LSD_K")) K = atoi(e) == 8 ? 8 : (atoi(e) == 16 ? 16 : K);  // development knob
+        const int sg_smem = K * (LSD_RING + SG_HASH) * (int)sizeof(u32);
+        static bool sg_attr = false;
+        if (!sg_attr) {
+            LE_CUDA(ctx, cudaFuncSetAttribute(k_lsd_grow_spec<16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              16 * (LSD_RING + SG_HASH) * (int)sizeof(u32)));
+            sg_attr = true;
+        }
+        if (K == 16)
+            k_lsd_grow_spec<16><<<n, 16 * 32, sg_smem, st>>>(img, (u32 *)ctx->lsd2.p, (u32 *)ctx->lsd7.p,
+                                                             (const float2 *)ctx->lsd6.p, (const u32 *)ctx->lsd3.p,
+                                                             (u32 *)ctx->lsd4.p, cnt, P, segs, width, prec_out, counts);
+        else
+            k_lsd_grow_spec<8><<<n, 8 * 32, sg_smem, st>>>(img, (u32 *)ctx->lsd2.p, (u32 *)ctx->lsd7.p,
+                                                           (const float2 *)ctx->lsd6.p, (const u32 *)ctx->lsd3.p,
+                                                           (u32 *)ctx->lsd4.p, cnt, P, segs, width, prec_out, counts);
+    } else
+        k_lsd_grow<<<n, 32, 0, st>>>(img, (u32 *)ctx->lsd2.p, (const float2 *)ctx->lsd6.p, (const u32 *)ctx->lsd3.p,
+                                     (u32 *)ctx->lsd4.p, cnt, P, segs, width, prec_out, counts);
     LE_T1(ctx, LE_K_LSD_GROW, st);
     LE_LAUNCH_CHECK(ctx);
     return LE_OK;

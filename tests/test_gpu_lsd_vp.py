@@ -216,3 +216,37 @@ def test_classify_and_camera_angles_run(engine, golden_inputs):
     assert np.isfinite(ph) and np.isfinite(th)
     ph, th = vp.get_camera_angles(img, 500, "lsd", 500)
     assert np.isfinite(ph) and np.isfinite(th)
+
+
+def test_lsd_speculative_equals_sequential_kernel():
+    """The K-warps-per-frame speculative region growing must reproduce the one-warp-per-frame kernel bit for bit
+    (segments, order, widths) -- run in subprocesses because the kernel choice is read once per process."""
+    import hashlib
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import sys, hashlib; sys.path.insert(0, %r)\n"
+        "import numpy as np, torch\n"
+        "import graphics_project_b200 as gp\n"
+        "eng = gp.Engine(0)\n"
+        "h = hashlib.sha1()\n"
+        "for kind, n, hh, ww in (('voxel', 6, 540, 960), ('cave', 5, 400, 600), ('cubes', 3, 270, 480)):\n"
+        "    u = gp.synth.make_batch(n, hh, ww, kind)\n"
+        "    gray = eng.bgr2gray(torch.from_numpy(np.stack(u)).cuda())\n"
+        "    for refine, scale in ((0, .8), (1, .8), (0, .5)):\n"
+        "        segs, width, prec, counts = eng.lsd(gray, refine=refine, scale=scale)\n"
+        "        c = counts.cpu().numpy(); h.update(c.tobytes())\n"
+        "        for i in range(n):\n"
+        "            h.update(segs[i, :c[i]].cpu().numpy().tobytes()); h.update(width[i, :c[i]].cpu().numpy().tobytes())\n"
+        "eng.check(); print('LSDHASH', h.hexdigest(), int(c.sum()))\n" % root)
+    outs = []
+    for env in ({"LE_LSD_SERIAL": "1"}, {"LE_LSD_K": "16"}, {"LE_LSD_K": "8"}):
+        e = dict(os.environ)
+        e.pop("LE_LSD_SERIAL", None)
+        e.update(env)
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=e, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs.append([l for l in r.stdout.splitlines() if l.startswith("LSDHASH")][0])
+    assert outs[0] == outs[1] == outs[2], outs
