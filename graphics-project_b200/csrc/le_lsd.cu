@@ -201,8 +201,50 @@ __global__ void __launch_bounds__(256) k_lsd_grad(const u8 *__restrict__ img, u3
     if ((threadIdx.x & 31) == 0 && smax > 0) atomicMax(&counters[f * LE_C_STRIDE + LE_C_MAX], smax);
 }
 
+// four pixels per thread for rows that are multiples of 4 bytes: two aligned words + one byte per row in,
+// one 16-byte store out
+__global__ void __launch_bounds__(256) k_lsd_grad4(const u8 *__restrict__ img, u32 *__restrict__ ang,
+                                                   int *__restrict__ counters, int H, int W, int s_thr)
+{
+    const int f = blockIdx.z;
+    const u8 *im = img + (size_t)f * H * W;
+    u32 *an = ang + (size_t)f * H * W;
+    const int x = 4 * (blockIdx.x * 32 + (threadIdx.x & 31)), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    int smax = 0;
+    if (x < W && y < H) {
+        u32 out[4] = {LSD_NOTDEF, LSD_NOTDEF, LSD_NOTDEF, LSD_NOTDEF};
+        if (y < H - 1) {
+            const u8 *r0 = im + (size_t)y * W + x, *r1 = r0 + W;
+            const u32 w0 = *(const u32 *)r0, w1 = *(const u32 *)r1;
+            const bool last = x + 4 >= W;  // the row's last word: its fourth pixel has no right neighbour
+            int a[5], b[5];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                a[k] = (int)((w0 >> (8 * k)) & 0xff);
+                b[k] = (int)((w1 >> (8 * k)) & 0xff);
+            }
+            a[4] = last ? 0 : (int)r0[4];
+            b[4] = last ? 0 : (int)r1[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                if (k == 3 && last) break;
+                const int DA = b[k + 1] - a[k], BC = a[k + 1] - b[k];
+                const int gx = DA + BC, gy = DA - BC;
+                const int s = gx * gx + gy * gy;
+                if (s > s_thr) {
+                    out[k] = __float_as_uint(d_fast_atan2((float)gx, (float)-gy));
+                    smax = max(smax, s);
+                }
+            }
+        }
+        *(uint4 *)(an + (size_t)y * W + x) = make_uint4(out[0], out[1], out[2], out[3]);
+    }
+    for (int o = 16; o; o >>= 1) smax = max(smax, __shfl_xor_sync(~0u, smax, o));
+    if ((threadIdx.x & 31) == 0 && smax > 0) atomicMax(&counters[f * LE_C_STRIDE + LE_C_MAX], smax);
+}
+
 // ------------------------------------------------------------------ 3: stable counting sort
-#define LS_CHUNK 2048
+#define LS_CHUNK 8192  // pixels per sort chunk (multiple of 128; a u16 chunk histogram holds up to 65535)
 static __device__ __forceinline__ int lsd_bin(int s, double bin_coef, int n_bins)
 {
     int b = (int)(sqrt((double)s / 4.0) * bin_coef);
@@ -1065,7 +1107,10 @@ extern "C" int le_lsd(le_ctx *ctx, const uint8_t *gray, int n, int h, int w, int
     int *cnt = (int *)ctx->counters.p;
     k_lsd_zero<<<(n + 255) / 256, 256, 0, st>>>(cnt, n);
     LE_LAUNCH_CHECK(ctx);
-    k_lsd_grad<<<dim3((W + 31) / 32, (H + 7) / 8, n), 256, 0, st>>>(img, (u32 *)ctx->lsd2.p, cnt, H, W, s_thr);
+    if ((W & 3) == 0 && (((size_t)img) & 3) == 0)
+        k_lsd_grad4<<<dim3((W / 4 + 31) / 32, (H + 7) / 8, n), 256, 0, st>>>(img, (u32 *)ctx->lsd2.p, cnt, H, W, s_thr);
+    else
+        k_lsd_grad<<<dim3((W + 31) / 32, (H + 7) / 8, n), 256, 0, st>>>(img, (u32 *)ctx->lsd2.p, cnt, H, W, s_thr);
     LE_LAUNCH_CHECK(ctx);
     u16 *chist = (u16 *)ctx->lsd5.p;
     u32 *coff = (u32 *)((char *)ctx->lsd5.p + sizeof(u16) * (size_t)nchunk * n_bins * n);
