@@ -710,6 +710,7 @@ __global__ void __launch_bounds__(32) k_lsd_grow(const u8 *__restrict__ img, u32
 //  * density refinement (refine >= 1) re-grows with another tolerance: only the first region of a round may do
 //    it (through the sequential code path); any other region that needs it waits to be first.
 #define SG_KMAX 16
+#define SG_ENT 96  // free seeds examined per round (slots + deferred)
 struct SgSlot {
     u32 seed;     // pixel index of the seed
     int ord_idx;  // its position in the ordered list
@@ -842,29 +843,53 @@ __global__ void __launch_bounds__(SG_K * 32) k_lsd_grow_spec(const u8 *__restric
     u32(*s_ring)[LSD_RING] = (u32(*)[LSD_RING])s_dyn;
     u32(*s_hset)[SG_HASH] = (u32(*)[SG_HASH])(s_dyn + SG_K * LSD_RING);
     __shared__ SgSlot s_slot[SG_K];
-    __shared__ int s_pos, s_k, s_nseg;
+    // the round's free seeds in list order: a slot id, or -1 = deferred (it touches an earlier seed of the round,
+    // so that seed's region almost surely swallows it; it is only looked at again at commit time)
+    __shared__ u32 s_ent_seed[SG_ENT], s_ent_xy[SG_ENT];
+    __shared__ int s_ent_ord[SG_ENT], s_ent_kind[SG_ENT];
+    __shared__ int s_pos, s_k, s_ne, s_nseg;
     if (threadIdx.x == 0) { s_pos = 0; s_nseg = 0; }
     __syncthreads();
     for (u32 round = 0;; round++) {
-        // ---- the next SG_K free seeds in order (warp 0)
+        // ---- the next free seeds in order (warp 0): SG_K of them get a warp, the ones touching an earlier seed
+        // of the round are deferred
         if (wid == 0) {
-            int k = 0, pos = s_pos;
-            while (k < SG_K && pos < ndef) {
+            int k = 0, ne = 0, pos = s_pos;
+            bool stop = false;
+            while (!stop && pos < ndef) {
                 const int i = pos + lane;
                 u32 pidx = i < ndef ? ord[i] : 0;
                 bool fr = i < ndef && !(ld_cg((const u32 *)an + pidx) & LSD_USED);
                 u32 m = __ballot_sync(~0u, fr);
-                const int rank = __popc(m & ((1u << lane) - 1));
-                if (fr && k + rank < SG_K) {
-                    s_slot[k + rank].seed = pidx;
-                    s_slot[k + rank].ord_idx = i;
+                while (m) {
+                    if (k == SG_K || ne == SG_ENT) { stop = true; break; }
+                    const int j = __ffs(m) - 1;
+                    m &= m - 1;
+                    const u32 pj = __shfl_sync(~0u, pidx, j);
+                    const int y = (int)(pj / (u32)W), x = (int)(pj - (u32)y * W);
+                    bool close = false;
+                    for (int e = lane; e < ne; e += 32) {
+                        const u32 q = s_ent_xy[e];
+                        close = close || (abs((int)(q & 0xffff) - x) <= 1 && abs((int)(q >> 16) - y) <= 1);
+                    }
+                    close = __any_sync(~0u, close);
+                    if (lane == 0) {
+                        s_ent_seed[ne] = pj;
+                        s_ent_xy[ne] = ((u32)y << 16) | (u32)x;
+                        s_ent_ord[ne] = pos + j;
+                        s_ent_kind[ne] = close ? -1 : k;
+                        if (!close) {
+                            s_slot[k].seed = pj;
+                            s_slot[k].ord_idx = pos + j;
+                        }
+                    }
+                    __syncwarp();
+                    if (!close) k++;
+                    ne++;
                 }
-                const int take = min(__popc(m), SG_K - k);
-                k += take;
-                if (k == SG_K) break;
                 pos += 32;
             }
-            if (lane == 0) s_k = k;
+            if (lane == 0) { s_k = k; s_ne = ne; }
         }
         __syncthreads();
         const int kc = s_k;
@@ -904,9 +929,15 @@ __global__ void __launch_bounds__(SG_K * 32) k_lsd_grow_spec(const u8 *__restric
         // ---- ordered commit (warp 0)
         if (wid == 0) {
             u32 bad = 0;
-            int w = 0;
             int nseg = s_nseg;
-            for (; w < kc; w++) {
+            const int ne = s_ne;
+            int e = 0;
+            for (; e < ne; e++) {
+                const int w = s_ent_kind[e];
+                if (w < 0) {  // deferred seed: swallowed by now (the usual case), or the round ends here
+                    if (ld_cg((const u32 *)an + s_ent_seed[e]) & LSD_USED) continue;
+                    break;
+                }
                 const SgSlot *S = &s_slot[w];
                 if (S->serial && w > 0) break;
                 if (w > 0 && (ld_cg((const u32 *)an + S->seed) & LSD_USED)) {  // swallowed by an earlier region of this round
@@ -958,7 +989,7 @@ __global__ void __launch_bounds__(SG_K * 32) k_lsd_grow_spec(const u8 *__restric
             }
             if (lane == 0) {
                 s_nseg = nseg;
-                s_pos = w < kc ? s_slot[w].ord_idx : s_slot[kc - 1].ord_idx + 1;
+                s_pos = e < ne ? s_ent_ord[e] : s_ent_ord[ne - 1] + 1;
             }
         }
         __syncthreads();
