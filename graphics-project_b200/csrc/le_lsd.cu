@@ -710,6 +710,10 @@ __global__ void __launch_bounds__(32) k_lsd_grow(const u8 *__restrict__ img, u32
 //  * density refinement (refine >= 1) re-grows with another tolerance: only the first region of a round may do
 //    it (through the sequential code path); any other region that needs it waits to be first.
 #define SG_KMAX 16
+#ifdef LSD_STATS
+__device__ int g_lsd_stats[16];
+__device__ long long g_lsd_cyc[8];
+#endif
 #define SG_ENT 96  // free seeds examined per round (slots + deferred)
 struct SgSlot {
     u32 seed;     // pixel index of the seed
@@ -817,7 +821,7 @@ static __device__ int lsd_grow_spec(volatile u32 *an, volatile u32 *own, const f
 }
 
 template <int SG_K>
-__global__ void __launch_bounds__(SG_K * 32) k_lsd_grow_spec(const u8 *__restrict__ img, u32 *__restrict__ ang,
+__global__ void __launch_bounds__(SG_K * 32, SG_K == 8 ? 4 : 1) k_lsd_grow_spec(const u8 *__restrict__ img, u32 *__restrict__ ang,
                                                              u32 *__restrict__ ownbuf,
                                                              const float2 *__restrict__ csbuf,
                                                              const u32 *__restrict__ order, u32 *__restrict__ regbuf,
@@ -850,48 +854,70 @@ __global__ void __launch_bounds__(SG_K * 32) k_lsd_grow_spec(const u8 *__restric
     __shared__ int s_pos, s_k, s_ne, s_nseg;
     if (threadIdx.x == 0) { s_pos = 0; s_nseg = 0; }
     __syncthreads();
+#ifdef LSD_STATS
+    long long t_sel = 0, t_grow = 0, t_com = 0, t0 = 0;
+#endif
     for (u32 round = 0;; round++) {
+#ifdef LSD_STATS
+        t0 = clock64();
+#endif
         // ---- the next free seeds in order (warp 0): SG_K of them get a warp, the ones touching an earlier seed
         // of the round are deferred
         if (wid == 0) {
             int k = 0, ne = 0, pos = s_pos;
             bool stop = false;
             while (!stop && pos < ndef) {
-                const int i = pos + lane;
-                u32 pidx = i < ndef ? ord[i] : 0;
-                bool fr = i < ndef && !(ld_cg((const u32 *)an + pidx) & LSD_USED);
-                u32 m = __ballot_sync(~0u, fr);
-                while (m) {
-                    if (k == SG_K || ne == SG_ENT) { stop = true; break; }
-                    const int j = __ffs(m) - 1;
-                    m &= m - 1;
-                    const u32 pj = __shfl_sync(~0u, pidx, j);
-                    const int y = (int)(pj / (u32)W), x = (int)(pj - (u32)y * W);
-                    bool close = false;
-                    for (int e = lane; e < ne; e += 32) {
-                        const u32 q = s_ent_xy[e];
-                        close = close || (abs((int)(q & 0xffff) - x) <= 1 && abs((int)(q >> 16) - y) <= 1);
-                    }
-                    close = __any_sync(~0u, close);
-                    if (lane == 0) {
-                        s_ent_seed[ne] = pj;
-                        s_ent_xy[ne] = ((u32)y << 16) | (u32)x;
-                        s_ent_ord[ne] = pos + j;
-                        s_ent_kind[ne] = close ? -1 : k;
-                        if (!close) {
-                            s_slot[k].seed = pj;
-                            s_slot[k].ord_idx = pos + j;
-                        }
-                    }
-                    __syncwarp();
-                    if (!close) k++;
-                    ne++;
+                // 128 list entries per trip: four seeds per lane, their USED flags fetched together
+                u32 pidx4[4];
+                bool fr4[4];
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const int i = pos + 32 * q + lane;
+                    pidx4[q] = i < ndef ? __ldg(ord + i) : 0;
                 }
-                pos += 32;
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const int i = pos + 32 * q + lane;
+                    fr4[q] = i < ndef && !(ld_cg((const u32 *)an + pidx4[q]) & LSD_USED);
+                }
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    u32 m = __ballot_sync(~0u, fr4[q]);
+                    while (m && !stop) {
+                        if (k == SG_K || ne == SG_ENT) { stop = true; break; }
+                        const int j = __ffs(m) - 1;
+                        m &= m - 1;
+                        const u32 pj = __shfl_sync(~0u, pidx4[q], j);
+                        const int y = (int)(pj / (u32)W), x = (int)(pj - (u32)y * W);
+                        bool close = false;
+                        for (int e = lane; e < ne; e += 32) {
+                            const u32 qq = s_ent_xy[e];
+                            close = close || (abs((int)(qq & 0xffff) - x) <= 1 && abs((int)(qq >> 16) - y) <= 1);
+                        }
+                        close = __any_sync(~0u, close);
+                        if (lane == 0) {
+                            s_ent_seed[ne] = pj;
+                            s_ent_xy[ne] = ((u32)y << 16) | (u32)x;
+                            s_ent_ord[ne] = pos + 32 * q + j;
+                            s_ent_kind[ne] = close ? -1 : k;
+                            if (!close) {
+                                s_slot[k].seed = pj;
+                                s_slot[k].ord_idx = pos + 32 * q + j;
+                            }
+                        }
+                        __syncwarp();
+                        if (!close) k++;
+                        ne++;
+                    }
+                }
+                pos += 128;
             }
             if (lane == 0) { s_k = k; s_ne = ne; }
         }
         __syncthreads();
+#ifdef LSD_STATS
+        t_sel += clock64() - t0; t0 = clock64();
+#endif
         const int kc = s_k;
         if (kc == 0) break;
         // ---- speculative growth, one warp per seed
@@ -926,46 +952,103 @@ __global__ void __launch_bounds__(SG_K * 32) k_lsd_grow_spec(const u8 *__restric
             }
         }
         __syncthreads();
+#ifdef LSD_STATS
+        t_grow += clock64() - t0; t0 = clock64();
+#endif
         // ---- ordered commit (warp 0)
         if (wid == 0) {
             u32 bad = 0;
             int nseg = s_nseg;
             const int ne = s_ne;
             int e = 0;
+#ifdef LSD_STATS
+            int st_commit = 0, st_void = 0, st_why = 0;
+            long long c_def = 0, c_seed = 0, c_val = 0, c_mark = 0, c_out = 0, c0;
+#define CT(x) do { long long c1 = clock64(); x += c1 - c0; c0 = c1; } while (0)
+            c0 = clock64();
+#else
+#define CT(x)
+#endif
             for (; e < ne; e++) {
                 const int w = s_ent_kind[e];
                 if (w < 0) {  // deferred seed: swallowed by now (the usual case), or the round ends here
-                    if (ld_cg((const u32 *)an + s_ent_seed[e]) & LSD_USED) continue;
+                    if (ld_cg((const u32 *)an + s_ent_seed[e]) & LSD_USED) { CT(c_def); continue; }
+#ifdef LSD_STATS
+                    st_why = 1;
+#endif
                     break;
                 }
                 const SgSlot *S = &s_slot[w];
+#ifdef LSD_STATS
+                if (S->serial && w > 0) { st_why = 2; break; }
+#else
                 if (S->serial && w > 0) break;
+#endif
                 if (w > 0 && (ld_cg((const u32 *)an + S->seed) & LSD_USED)) {  // swallowed by an earlier region of this round
                     bad |= 1u << w;
+#ifdef LSD_STATS
+                    st_void++;
+#endif
+                    CT(c_seed);
                     continue;
                 }
+                CT(c_seed);
                 int n = S->n;
                 const u32 *rg = w == 0 ? reg0 : reg0 + npx + (size_t)(w - 1) * cap_w;
                 if (w > 0) {
+#ifdef LSD_STATS
+                    if (bad == ~0u || (S->relied & bad)) { st_why = 3; break; }
+                    if (S->need_refine) { st_why = 4; break; }
+#else
                     if (bad == ~0u || (S->relied & bad)) break;
                     if (S->need_refine) break;
-                    // every pixel must still be free: all earlier regions of the round are committed by now
+#endif
+                    // every pixel must still be free: all earlier regions of the round are committed by now.
+                    // 256 pixels per trip (eight per lane): the list entries, then their words, are fetched
+                    // together -- two memory rounds per trip instead of two per 32 pixels
                     bool ok = true;
-                    for (int i = lane; i < n; i += 32) {
-                        u32 pt = ld_cg(rg + i);
-                        size_t p = (size_t)(pt >> 16) * W + (pt & 0xffff);
-                        ok = ok && !(ld_cg((const u32 *)an + p) & LSD_USED);
+                    u32 pt[8], av[8];
+                    for (int base = 0; base < n; base += 256) {
+#pragma unroll
+                        for (int q = 0; q < 8; q++) {
+                            const int i = base + 32 * q + lane;
+                            pt[q] = i < n ? ld_cg(rg + i) : 0xFFFFFFFFu;
+                        }
+#pragma unroll
+                        for (int q = 0; q < 8; q++)
+                            av[q] = pt[q] != 0xFFFFFFFFu ? ld_cg((const u32 *)an + (size_t)(pt[q] >> 16) * W + (pt[q] & 0xffff)) : 0u;
+#pragma unroll
+                        for (int q = 0; q < 8; q++) ok = ok && !(av[q] & LSD_USED);
                     }
+#ifdef LSD_STATS
+                    if (!__all_sync(~0u, ok)) { st_why = 5; break; }
+                    st_commit++;
+                    CT(c_val);
+#else
                     if (!__all_sync(~0u, ok)) break;
-                }
-                if (w > 0) {
-                    for (int i = lane; i < n; i += 32) {
-                        u32 pt = ld_cg(rg + i);
-                        size_t p = (size_t)(pt >> 16) * W + (pt & 0xffff);
-                        an[p] = ld_cg((const u32 *)an + p) | LSD_USED;
+#endif
+                    if (n <= 256) {  // still in registers
+#pragma unroll
+                        for (int q = 0; q < 8; q++)
+                            if (pt[q] != 0xFFFFFFFFu) an[(size_t)(pt[q] >> 16) * W + (pt[q] & 0xffff)] = av[q] | LSD_USED;
+                    } else {
+                        for (int base = 0; base < n; base += 256) {
+#pragma unroll
+                            for (int q = 0; q < 8; q++) {
+                                const int i = base + 32 * q + lane;
+                                pt[q] = i < n ? ld_cg(rg + i) : 0xFFFFFFFFu;
+                            }
+#pragma unroll
+                            for (int q = 0; q < 8; q++)
+                                av[q] = pt[q] != 0xFFFFFFFFu ? ld_cg((const u32 *)an + (size_t)(pt[q] >> 16) * W + (pt[q] & 0xffff)) : 0u;
+#pragma unroll
+                            for (int q = 0; q < 8; q++)
+                                if (pt[q] != 0xFFFFFFFFu) an[(size_t)(pt[q] >> 16) * W + (pt[q] & 0xffff)] = av[q] | LSD_USED;
+                        }
                     }
                 }
                 __syncwarp();
+                CT(c_mark);
                 if ((unsigned)n < P.min_reg_size) continue;
                 LsdRect rec = S->rec;
                 double reg_angle = S->reg_angle;
@@ -986,15 +1069,43 @@ __global__ void __launch_bounds__(SG_K * 32) k_lsd_grow_spec(const u8 *__restric
                     if (precs) precs[(size_t)f * P.max_segs + nseg] = P.p;
                 }
                 nseg++;
+                CT(c_out);
             }
+#ifdef LSD_STATS
+            if (lane == 0 && f == 0) {
+                atomicAdd((unsigned long long *)&g_lsd_cyc[0], (unsigned long long)c_def); atomicAdd((unsigned long long *)&g_lsd_cyc[1], (unsigned long long)c_seed);
+                atomicAdd((unsigned long long *)&g_lsd_cyc[2], (unsigned long long)c_val); atomicAdd((unsigned long long *)&g_lsd_cyc[3], (unsigned long long)c_mark);
+                atomicAdd((unsigned long long *)&g_lsd_cyc[4], (unsigned long long)c_out);
+            }
+#endif
             if (lane == 0) {
                 s_nseg = nseg;
                 s_pos = e < ne ? s_ent_ord[e] : s_ent_ord[ne - 1] + 1;
+#ifdef LSD_STATS
+                if (f == 0) {
+                    atomicAdd(&g_lsd_stats[0], 1); atomicAdd(&g_lsd_stats[1], kc); atomicAdd(&g_lsd_stats[2], ne);
+                    atomicAdd(&g_lsd_stats[3], st_commit); atomicAdd(&g_lsd_stats[4], st_void); atomicAdd(&g_lsd_stats[5 + st_why], 1);
+                }
+#endif
             }
         }
+#ifdef LSD_STATS
+        if (threadIdx.x == 0 && f == 0) atomicAdd((unsigned long long *)&g_lsd_cyc[5], (unsigned long long)(clock64() - t0));
+        if (threadIdx.x == 32 && f == 0) atomicAdd((unsigned long long *)&g_lsd_cyc[6], (unsigned long long)(clock64() - t0));
+#endif
         __syncthreads();
+#ifdef LSD_STATS
+        t_com += clock64() - t0;
+#endif
     }
     if (threadIdx.x == 0) counts[f] = s_nseg;
+#ifdef LSD_STATS
+    if (threadIdx.x == 0 && f == 0) printf("LSDCYCLES select %lld grow %lld commit %lld (deferred %lld seedchk %lld validate %lld mark %lld out %lld) w0-before-sync %lld w1-before-sync %lld\n", t_sel, t_grow, t_com, g_lsd_cyc[0], g_lsd_cyc[1], g_lsd_cyc[2], g_lsd_cyc[3], g_lsd_cyc[4], g_lsd_cyc[5], g_lsd_cyc[6]);
+    if (threadIdx.x == 0 && f == 0)
+        printf("LSDSTATS rounds %d slots %d entries %d commits(w>0) %d voids %d | end: all-resolved %d deferred-free %d serial %d relied %d refine %d used %d\n",
+               g_lsd_stats[0], g_lsd_stats[1], g_lsd_stats[2], g_lsd_stats[3], g_lsd_stats[4], g_lsd_stats[5], g_lsd_stats[6],
+               g_lsd_stats[7], g_lsd_stats[8], g_lsd_stats[9], g_lsd_stats[10]);
+#endif
 }
 
 // ------------------------------------------------------------------ host side
@@ -1161,9 +1272,9 @@ extern "C" int le_lsd(le_ctx *ctx, const uint8_t *gray, int n, int h, int w, int
     LE_T0(ctx, LE_K_LSD_GROW, st);
     if (spec) {
         LE_CUDA(ctx, cudaMemsetAsync(ctx->lsd7.p, 0, sizeof(u32) * npx * n, st));
-        // warps per frame: 16 while every frame's CTA is resident at once (2 per SM: registers and the pixel sets'
-        // shared memory), 8 for bigger batches (4 per SM) -- a second wave costs more than the narrower round
-        int K = n <= 2 * ctx->sm_count ? 16 : 8;
+        // warps per frame: 16 while every frame can have an SM of its own, else 8 (four CTAs per SM, 64 registers):
+        // a second wave of CTAs costs more than the narrower rounds
+        int K = n <= ctx->sm_count ? 16 : 8;
         if (const char *e = getenv("LE_LSD_K")) K = atoi(e) == 8 ? 8 : (atoi(e) == 16 ? 16 : K);  // development knob
         const int sg_smem = K * (LSD_RING + SG_HASH) * (int)sizeof(u32);
         static bool sg_attr = false;
