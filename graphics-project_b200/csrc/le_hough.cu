@@ -212,6 +212,7 @@ k_hough_vote(const u32 *__restrict__ queue, int *__restrict__ counters, const fl
     const u32 inc = (a & 1) ? 0x10000u : 1u;
     float4 *stage = (float4 *)s_stage[warp];  // two staged pixels (x0, y0, x1, y1) per entry
     const float rw = 1.0f / (float)w;
+    const bool small = npx <= ((size_t)1 << 24);
     auto vote = [&](float x, float y, bool on) {
         const float t = __fadd_rn(__fadd_rn(__fmul_rn(x, tcos), __fmul_rn(y, tsin)), MAGIC);
         const u32 sa = (u32)__float_as_int(t) * (2u * A) + kaddr;
@@ -225,8 +226,13 @@ k_hough_vote(const u32 *__restrict__ queue, int *__restrict__ counters, const fl
         int p = idx < nedge ? (int)q[idx] : 0;
         int py = (int)((float)p * rw);  // estimate of p / w, then exact correction
         int px = p - py * w;
-        while (px < 0) { px += w; py--; }
-        while (px >= w) { px -= w; py++; }
+        if (small) {  // p < 2^24 is exact in float and the estimate is off by one at most: two selects, no loop
+            if (px < 0) { px += w; py--; }
+            if (px >= w) { px -= w; py++; }
+        } else {
+            while (px < 0) { px += w; py--; }
+            while (px >= w) { px -= w; py++; }
+        }
         __syncwarp();
         s_stage[warp][lane] = make_float2((float)px, (float)py);
         __syncwarp();
@@ -343,9 +349,14 @@ k_hough_vote(const u32 *__restrict__ queue, int *__restrict__ counters, const fl
     }
     __shared__ int s_last;
     // ---- the last CTA of the frame to get here orders the frame's peaks (its histogram is free by then)
-    __threadfence();  // this thread's peak keys are visible before the CTA signals
+    // The CTA's rows and peak keys must be visible before it signals: the barrier orders every thread's writes
+    // before thread 0's fence, which is cumulative (the grid-sync pattern).  One fence per CTA instead of one per
+    // warp: MEMBAR.SC + CCTL.IVALL in all 32 warps held 12 % of the kernel's stall samples.
     __syncthreads();
-    if (tid == 0) s_last = atomicAdd(&cnt[LE_C_AUX0], 1) == (int)gridDim.x - 1;
+    if (tid == 0) {
+        __threadfence();
+        s_last = atomicAdd(&cnt[LE_C_AUX0], 1) == (int)gridDim.x - 1;
+    }
     __syncthreads();
     if (s_last) {
         __threadfence();
