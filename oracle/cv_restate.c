@@ -728,14 +728,179 @@ static int lsd_refine(LsdState *s, RegPt *reg, int *pn, double *reg_angle, doubl
     return 1;
 }
 
-/* LSD on a u8 gray image, refine in {0,1}.  lines: 4 f32 per segment; width/prec f64 (optional).
+
+/* ---- refine = LSD_REFINE_ADV: number of false alarms of a rectangle.
+ * nfa() and the two log-gamma approximations are the published LSD formulas; they are pinned exactly: every NFA
+ * value cv2 4.13 returns for an unimproved rectangle inverts to an integer pair (points, aligned points).
+ * The rectangle's pixel enumeration below is what those pairs identify: rows y = ceil(min vertex y) ..
+ * ceil(max vertex y); in a row the pixels ceil(left) .. floor(right), both limits evaluated directly from a
+ * vertex and a slope (nothing is accumulated); the right limit changes edge at the first row at or below its
+ * vertex, the LEFT limit one row later (that row still extrapolates the first left edge -- for a
+ * near-horizontal rectangle this adds up to a row's worth of pixels, and cv2 does the same).  PARTIALLY PINNED:
+ * it reproduces the pairs of 2295 of the 2333 unimproved rectangles of the 19 cube fixtures (both scales); the
+ * other 38 are thin, nearly axis-aligned rectangles whose top vertex is the right one, where cv2 is also late
+ * on the right limit in some cases (tests/test_oracle.py::test_lsd_refine2_vs_cv2 states the resulting
+ * segment-level agreement). */
+static double lsd_log_gamma(double x)
+{
+    if (x > 15.0) /* Windschitl */
+        return 0.918938533204673 + (x - 0.5) * log(x) - x + 0.5 * x * log(x * sinh(1 / x) + 1 / (810.0 * pow(x, 6.0)));
+    static const double q[7] = {75122.6331530, 80916.6278952, 36308.2951477, 8687.24529705, 1168.92649479,
+                                83.8676043424, 2.50662827511};
+    double a = (x + 0.5) * log(x + 5.5) - (x + 5.5);
+    double b = 0;
+    for (int n = 0; n < 7; ++n) {
+        a -= log(x + (double)n);
+        b += q[n] * pow(x, (double)n);
+    }
+    return a + log(b);
+}
+
+static int lsd_double_equal(double a, double b)
+{
+    if (a == b) return 1;
+    double abs_diff = fabs(a - b), aa = fabs(a), bb = fabs(b);
+    double abs_max = (aa > bb) ? aa : bb;
+    if (abs_max < DBL_MIN) abs_max = DBL_MIN;
+    return (abs_diff / abs_max) <= (100.0 * DBL_EPSILON);
+}
+
+double or_lsd_nfa(int n, int k, double p, double LOG_NT)
+{
+    if (n == 0 || k == 0) return -LOG_NT;
+    if (n == k) return -LOG_NT - (double)n * log10(p);
+    double p_term = p / (1 - p);
+    double log1term = lsd_log_gamma((double)n + 1) - lsd_log_gamma((double)k + 1) - lsd_log_gamma((double)(n - k) + 1) +
+                      (double)k * log(p) + (double)(n - k) * log(1.0 - p);
+    double term = exp(log1term);
+    if (lsd_double_equal(term, 0)) {
+        if (k > n * p) return -log1term / M_LN10 - LOG_NT;
+        else return -LOG_NT;
+    }
+    double bin_tail = term;
+    double tolerance = 0.1;
+    for (int i = k + 1; i <= n; ++i) {
+        double bin_term = (double)(n - i + 1) / (double)i;
+        double mult_term = bin_term * p_term;
+        term *= mult_term;
+        bin_tail += term;
+        if (bin_term < 1) {
+            double err = term * ((1 - pow(mult_term, (double)(n - i + 1))) / (1 - mult_term) - 1);
+            if (err < tolerance * fabs(-log10(bin_tail) - LOG_NT) * bin_tail) break;
+        }
+    }
+    return -log10(bin_tail) - LOG_NT;
+}
+
+static int g_last_n, g_last_k;
+static double lsd_rect_nfa(const LsdState *s, const LsdRect *rec, double LOG_NT)
+{
+    int total_pts = 0, alg_pts = 0;
+    const double hw = rec->width / 2.0, dyhw = rec->dy * hw, dxhw = rec->dx * hw;
+    /* the four vertices in rotation order; m = the topmost one, its two neighbours head the left and right chains */
+    const double vx[4] = {rec->x1 - dyhw, rec->x2 - dyhw, rec->x2 + dyhw, rec->x1 + dyhw};
+    const double vy[4] = {rec->y1 + dxhw, rec->y2 + dxhw, rec->y2 - dxhw, rec->y1 - dxhw};
+    int m = 0;
+    for (int i = 1; i < 4; i++)
+        if (vy[i] < vy[m]) m = i;
+    const int a1 = (m + 1) & 3, b1 = (m + 3) & 3, op = (m + 2) & 3;
+    const int ha = vy[m] == vy[a1], hb = vy[m] == vy[b1];
+    const double sa = ha ? 0.0 : (vx[m] - vx[a1]) / (vy[m] - vy[a1]), sb = hb ? 0.0 : (vx[m] - vx[b1]) / (vy[m] - vy[b1]);
+    const int a_left = (ha || hb) ? vx[a1] < vx[b1] : sa < sb;
+    const int L1 = a_left ? a1 : b1, R1 = a_left ? b1 : a1;
+    const double fl = a_left ? sa : sb, fr = a_left ? sb : sa;
+    const double sl = vy[L1] == vy[op] ? 0.0 : (vx[L1] - vx[op]) / (vy[L1] - vy[op]);
+    const double sr = vy[R1] == vy[op] ? 0.0 : (vx[R1] - vx[op]) / (vy[R1] - vy[op]);
+    const double ya_d = ceil(vy[m]), yb_d = ceil(vy[op]);
+    int ya = (int)fmax(fmin(ya_d, 1e9), -1e9), yb = (int)fmax(fmin(yb_d, 1e9), -1e9);
+    if (yb > s->H - 1) yb = s->H - 1;
+    for (int y = ya < 0 ? 0 : ya; y <= yb; ++y) {
+        const int l2 = ((double)(y - 1) >= vy[L1]) || vy[L1] <= ya_d; /* the left limit changes edge one row late */
+        const int r2 = (double)y >= vy[R1];
+        const double lx = l2 ? vx[L1] + ((double)y - vy[L1]) * sl : vx[m] + ((double)y - vy[m]) * fl;
+        const double rx = r2 ? vx[R1] + ((double)y - vy[R1]) * sr : vx[m] + ((double)y - vy[m]) * fr;
+        const double a_d = ceil(lx), b_d = floor(rx);
+        const int a = !(a_d > 0) ? 0 : (int)fmin(a_d, 1e9);
+        const int b = !(b_d < s->W - 1) ? s->W - 1 : (int)fmax(b_d, -1e9);
+        for (int x = a; x <= b; ++x) {
+            ++total_pts;
+            if (lsd_aligned(s, x, y, rec->theta, rec->prec)) ++alg_pts;
+        }
+    }
+    g_last_n = total_pts; g_last_k = alg_pts;
+    return or_lsd_nfa(total_pts, alg_pts, rec->p, LOG_NT);
+}
+
+static double lsd_rect_improve(const LsdState *s, LsdRect *rec, double LOG_NT, double LOG_EPS)
+{
+    const double delta = 0.5, delta_2 = delta / 2.0;
+    double log_nfa = lsd_rect_nfa(s, rec, LOG_NT);
+    if (log_nfa > LOG_EPS) return log_nfa;
+    LsdRect r = *rec; /* finer precision */
+    for (int n = 0; n < 5; ++n) {
+        r.p /= 2;
+        r.prec = r.p * M_PI;
+        double v = lsd_rect_nfa(s, &r, LOG_NT);
+        if (v > log_nfa) { log_nfa = v; *rec = r; }
+    }
+    if (log_nfa > LOG_EPS) return log_nfa;
+    r = *rec; /* reduce width */
+    for (int n = 0; n < 5; ++n) {
+        if ((r.width - delta) >= 0.5) {
+            r.width -= delta;
+            double v = lsd_rect_nfa(s, &r, LOG_NT);
+            if (v > log_nfa) { *rec = r; log_nfa = v; }
+        }
+    }
+    if (log_nfa > LOG_EPS) return log_nfa;
+    r = *rec; /* reduce one side */
+    for (int n = 0; n < 5; ++n) {
+        if ((r.width - delta) >= 0.5) {
+            r.x1 += -r.dy * delta_2; r.y1 += r.dx * delta_2;
+            r.x2 += -r.dy * delta_2; r.y2 += r.dx * delta_2;
+            r.width -= delta;
+            double v = lsd_rect_nfa(s, &r, LOG_NT);
+            if (v > log_nfa) { *rec = r; log_nfa = v; }
+        }
+    }
+    if (log_nfa > LOG_EPS) return log_nfa;
+    r = *rec; /* reduce the other side */
+    for (int n = 0; n < 5; ++n) {
+        if ((r.width - delta) >= 0.5) {
+            r.x1 -= -r.dy * delta_2; r.y1 -= r.dx * delta_2;
+            r.x2 -= -r.dy * delta_2; r.y2 -= r.dx * delta_2;
+            r.width -= delta;
+            double v = lsd_rect_nfa(s, &r, LOG_NT);
+            if (v > log_nfa) { *rec = r; log_nfa = v; }
+        }
+    }
+    if (log_nfa > LOG_EPS) return log_nfa;
+    r = *rec; /* even finer precision */
+    for (int n = 0; n < 5; ++n) {
+        if ((r.width - delta) >= 0.5) {
+            r.p /= 2;
+            r.prec = r.p * M_PI;
+            double v = lsd_rect_nfa(s, &r, LOG_NT);
+            if (v > log_nfa) { log_nfa = v; *rec = r; }
+        }
+    }
+    return log_nfa;
+}
+
+static double *g_nfa_out = 0, *g_rect_out = 0;
+/* optional debug output: 12 doubles per emitted segment (x1 y1 x2 y2 width dx dy theta prec p, then the point
+ * count and aligned count of the rectangle's last NFA evaluation) */
+void or_lsd_set_rect_out(double *p) { g_rect_out = p; }
+/* optional NFA output of the next or_lsd call(s) with refine = 2 (one double per segment) */
+void or_lsd_set_nfa_out(double *p) { g_nfa_out = p; }
+
+/* LSD on a u8 gray image, refine in {0,1,2}.  lines: 4 f32 per segment; width/prec f64 (optional).
  * Optional debug outputs: scaled_out (dh*dw u8), angles_out (dh*dw f64).
  * Returns number of segments (only max_segs written). */
 int or_lsd(const u8 *gray, int h, int w, int refine, double scale, double sigma_scale, double quant, double ang_th,
            double log_eps, double density_th, int n_bins, float *lines, double *widths, double *precs, int max_segs,
            u8 *scaled_out, double *angles_out)
 {
-    (void)log_eps;
     const double prec = M_PI * ang_th / 180;
     const double p = ang_th / 180;
     const double rho = quant / sin(prec);
@@ -804,9 +969,19 @@ int or_lsd(const u8 *gray, int h, int w, int refine, double scale, double sigma_
         int n = lsd_region_grow(&st, pidx % W, pidx / W, reg, &reg_angle, prec);
         if ((size_t)n < min_reg_size) continue;
         LsdRect rec;
+        double log_nfa = -1;
         lsd_region2rect(reg, n, reg_angle, prec, p, &rec);
         if (refine > 0) {
             if (!lsd_refine(&st, reg, &n, &reg_angle, prec, p, &rec, density_th)) continue;
+            if (refine >= 2) {
+                log_nfa = lsd_rect_improve(&st, &rec, LOG_NT, log_eps);
+                if (log_nfa <= log_eps) continue;
+            }
+        }
+        if (g_rect_out && nseg < max_segs) {
+            double *o = g_rect_out + 12 * nseg;
+            o[0] = rec.x1; o[1] = rec.y1; o[2] = rec.x2; o[3] = rec.y2; o[4] = rec.width; o[5] = rec.dx; o[6] = rec.dy;
+            o[7] = rec.theta; o[8] = rec.prec; o[9] = rec.p; o[10] = g_last_n; o[11] = g_last_k;
         }
         rec.x1 += 0.5; rec.y1 += 0.5; rec.x2 += 0.5; rec.y2 += 0.5;
         if (scale != 1) { rec.x1 /= scale; rec.y1 /= scale; rec.x2 /= scale; rec.y2 /= scale; rec.width /= scale; }
@@ -815,6 +990,7 @@ int or_lsd(const u8 *gray, int h, int w, int refine, double scale, double sigma_
             lines[4 * nseg + 2] = (float)rec.x2; lines[4 * nseg + 3] = (float)rec.y2;
             if (widths) widths[nseg] = rec.width;
             if (precs) precs[nseg] = rec.p;
+            if (g_nfa_out) g_nfa_out[nseg] = log_nfa;
         }
         nseg++;
     }

@@ -169,14 +169,16 @@ def lsd_scale_image(gray, scale=0.8, sigma_scale=0.6):
 
 
 def lsd(gray, refine=0, scale=0.8, sigma_scale=0.6, quant=2.0, ang_th=22.5, log_eps=0.0, density_th=0.7,
-        n_bins=1024, max_segs=1 << 16, return_debug=False):
-    """-> (lines (N,1,4) f32 or None, width (N,1) f64, prec (N,1) f64)"""
-    assert refine in (0, 1), "oracle restates LSD_REFINE_NONE/STD only"
+        n_bins=1024, max_segs=1 << 16, return_debug=False, return_nfa=False):
+    """-> (lines (N,1,4) f32 or None, width (N,1) f64, prec (N,1) f64[, nfa (N,1) f64 with return_nfa]).
+    refine 0 / 1 are pinned bit for bit; refine 2 (LSD_REFINE_ADV) is partially pinned (cv_restate.c)."""
+    assert refine in (0, 1, 2)
     gray = _u8(gray)
     h, w = gray.shape
     lines = np.empty((max_segs, 4), np.float32)
     wd = np.empty(max_segs, np.float64)
     pr = np.empty(max_segs, np.float64)
+    nf = np.full(max_segs, -1.0, np.float64)
     dbg_s = dbg_a = None
     if return_debug:
         dh, dw = C.c_int(h), C.c_int(w)
@@ -184,13 +186,19 @@ def lsd(gray, refine=0, scale=0.8, sigma_scale=0.6, quant=2.0, ang_th=22.5, log_
             lib().or_lsd_scaled_dims(C.c_int(h), C.c_int(w), C.c_double(scale), C.byref(dh), C.byref(dw))
         dbg_s = np.empty((dh.value, dw.value), np.uint8)
         dbg_a = np.empty((dh.value, dw.value), np.float64)
-    n = lib().or_lsd(_p(gray), C.c_int(h), C.c_int(w), C.c_int(refine), C.c_double(scale), C.c_double(sigma_scale),
-                     C.c_double(quant), C.c_double(ang_th), C.c_double(log_eps), C.c_double(density_th),
-                     C.c_int(n_bins), _p(lines), _p(wd), _p(pr), C.c_int(max_segs),
-                     _p(dbg_s) if return_debug else None, _p(dbg_a) if return_debug else None)
+    lib().or_lsd_set_nfa_out(_p(nf))
+    try:
+        n = lib().or_lsd(_p(gray), C.c_int(h), C.c_int(w), C.c_int(refine), C.c_double(scale), C.c_double(sigma_scale),
+                         C.c_double(quant), C.c_double(ang_th), C.c_double(log_eps), C.c_double(density_th),
+                         C.c_int(n_bins), _p(lines), _p(wd), _p(pr), C.c_int(max_segs),
+                         _p(dbg_s) if return_debug else None, _p(dbg_a) if return_debug else None)
+    finally:
+        lib().or_lsd_set_nfa_out(None)
     assert n <= max_segs
     if n == 0:
-        res = (None, None, None)
+        res = (None, None, None) + ((None,) if return_nfa else ())
     else:
         res = (lines[:n].reshape(n, 1, 4).copy(), wd[:n].reshape(n, 1).copy(), pr[:n].reshape(n, 1).copy())
+        if return_nfa:
+            res = res + (nf[:n].reshape(n, 1).copy(),)
     return res + (dbg_s, dbg_a) if return_debug else res
