@@ -112,7 +112,8 @@ def test_shim_rejects_off_path_parameters_without_gpu():
     with pytest.raises(cv.error):
         cv.GaussianBlur(img, (7, 7), 0)
     with pytest.raises(cv.error):
-        cv.createLineSegmentDetector(2)
+        cv.createLineSegmentDetector(3)
+    assert cv.createLineSegmentDetector(2).params["refine"] == 2  # LSD_REFINE_ADV is on the path
     assert cv.COLOR_BGR2GRAY == 6 and cv.NORM_MINMAX == 32
     assert callable(cv.imread)  # non-hot-path attributes are forwarded to the real cv2
 
