@@ -28,6 +28,32 @@ for (n, h, w, kind) in ((256, 1080, 1920, "cubes"), (1024, 1080, 1920, "cubes"),
     out.append({"chain": "prob: Canny(5,150)+HoughLinesP(30,50,10)", "n": n, "h": h, "w": w, "ms": round(ms, 3), "fps": round(n / ms * 1e3), "kernels_ms": kt, "segs_mean": float(counts.float().mean())})
     print(json.dumps(out[-1]), flush=True)
     del t, edges
+# Canny + standard HoughLines (the bench.py chain) at 4K, with the accumulator written
+for (n, h, w) in ((64, 2160, 3840),):
+    t = frames(n, h, w, "cubes")
+    na, nr = eng.hough_dims(h, w)
+    edges = torch.empty((n, h, w), dtype=torch.uint8, device="cuda")
+    outs = (torch.empty((n, 1024, 2), dtype=torch.float32, device="cuda"), None, torch.empty((n,), dtype=torch.int32, device="cuda"),
+            torch.empty((n, na + 2, nr + 2), dtype=torch.int32, device="cuda"))
+    run = lambda: (eng.front_canny(t, 5, 10, blur=True, out=edges), eng.hough_lines(None, 1.0, np.pi / 180, 50, out=outs))
+    run(); eng.timing(True); eng.timing_read()
+    ms = timeit(run, reps=5)
+    kt = {k: round(v[0]/v[1], 3) for k, v in eng.timing_read().items()}; eng.timing(False)
+    alg = 4 * w * h + 4 * (na + 2) * (nr + 2)
+    out.append({"chain": "Canny(5,10)+blur+HoughLines(50), accumulator written", "n": n, "h": h, "w": w, "ms": round(ms, 3),
+                "fps": round(n / ms * 1e3), "kernels_ms": kt, "algorithmic_bytes_per_frame": alg,
+                "frac_of_measured_hbm_6549.8": round(alg * n / (ms * 1e-3) / 1e9 / 6549.8, 3), "lines_mean": float(outs[2].float().mean())})
+    print(json.dumps(out[-1]), flush=True)
+    del t, edges, outs
+# LSD_REFINE_ADV at the simulator's parameters (opencv.py:142-145)
+t = frames(128, 1080, 1920, "voxel"); gray = eng.bgr2gray(t); del t
+eng.lsd(gray, refine=2, scale=.5); eng.timing(True); eng.timing_read()
+ms = timeit(lambda: eng.lsd(gray, refine=2, scale=.5), reps=2)
+kt = {k: round(v[0]/v[1], 3) for k, v in eng.timing_read().items()}; eng.timing(False)
+segs, _, _, counts = eng.lsd(gray, refine=2, scale=.5)
+out.append({"chain": "lsd(refine 2, scale .5)", "kind": "voxel", "n": 128, "h": 1080, "w": 1920, "ms": round(ms, 3), "fps": round(128 / ms * 1e3), "kernels_ms": kt, "segs_mean": float(counts.float().mean())})
+print(json.dumps(out[-1]), flush=True)
+del gray
 for (n, h, w, kind) in ((128, 1080, 1920, "voxel"), (512, 1080, 1920, "voxel"), (512, 1080, 1920, "cave")):
     t = frames(n, h, w, kind)
     gray = eng.bgr2gray(t); del t
