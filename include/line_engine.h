@@ -115,8 +115,8 @@ int le_hough_lines_p(le_ctx *ctx, const uint8_t *edges, int n, int h, int w, dou
  * refine 0 (LSD_REFINE_NONE), 1 (LSD_REFINE_STD), 2 (LSD_REFINE_ADV: rectangle improvement + NFA validation
  * against log_eps).  segs: float32 [n][max_segs][4]; width, prec (optional): float64 [n][max_segs];
  * nfa (optional, written for refine 2 only): float64 [n][max_segs] = cv2's fourth output; counts: int32 [n].
- * Parity: refine 0 / 1 reproduce cv2 4.13 bit for bit including order; refine 2 reproduces 99.4 % of cv2's
- * segments bit for bit (its rectangle pixel count is pinned for 98.4 % of the rectangles). */
+ * Parity: all three modes reproduce cv2 4.13 including order (segments, widths, precisions, NFA values; the
+ * rectangle's cos / sin are evaluated in double-double so that its vertices equal glibc's). */
 int le_lsd_scaled_dims(int h, int w, double scale, int *sh, int *sw);
 int le_lsd(le_ctx *ctx, const uint8_t *gray, int n, int h, int w, int refine, double scale, double sigma_scale,
            double quant, double ang_th, double log_eps, double density_th, int n_bins, float *segs, double *width,

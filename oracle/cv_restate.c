@@ -732,15 +732,14 @@ static int lsd_refine(LsdState *s, RegPt *reg, int *pn, double *reg_angle, doubl
 /* ---- refine = LSD_REFINE_ADV: number of false alarms of a rectangle.
  * nfa() and the two log-gamma approximations are the published LSD formulas; they are pinned exactly: every NFA
  * value cv2 4.13 returns for an unimproved rectangle inverts to an integer pair (points, aligned points).
- * The rectangle's pixel enumeration below is what those pairs identify: rows y = ceil(min vertex y) ..
+ * The rectangle's pixel enumeration below is what those pairs identify, and it reproduces ALL of them (2333 of
+ * 2333 unimproved rectangles of the 19 cube fixtures at both scales; then every refine-2 output of the 21
+ * fixtures, tests/test_lsd2_oracle.py): the topmost vertex (ties: the left one) heads a left and a right chain
+ * of two edges each; an edge that crosses no integer row has slope 0; rows y = ceil(min vertex y) ..
  * ceil(max vertex y); in a row the pixels ceil(left) .. floor(right), both limits evaluated directly from a
  * vertex and a slope (nothing is accumulated); the right limit changes edge at the first row at or below its
  * vertex, the LEFT limit one row later (that row still extrapolates the first left edge -- for a
- * near-horizontal rectangle this adds up to a row's worth of pixels, and cv2 does the same).  PARTIALLY PINNED:
- * it reproduces the pairs of 2295 of the 2333 unimproved rectangles of the 19 cube fixtures (both scales); the
- * other 38 are thin, nearly axis-aligned rectangles whose top vertex is the right one, where cv2 is also late
- * on the right limit in some cases (tests/test_oracle.py::test_lsd_refine2_vs_cv2 states the resulting
- * segment-level agreement). */
+ * near-horizontal rectangle this adds up to a row's worth of pixels, and cv2 does the same). */
 static double lsd_log_gamma(double x)
 {
     if (x > 15.0) /* Windschitl */
@@ -800,22 +799,23 @@ static double lsd_rect_nfa(const LsdState *s, const LsdRect *rec, double LOG_NT)
     /* the four vertices in rotation order; m = the topmost one, its two neighbours head the left and right chains */
     const double vx[4] = {rec->x1 - dyhw, rec->x2 - dyhw, rec->x2 + dyhw, rec->x1 + dyhw};
     const double vy[4] = {rec->y1 + dxhw, rec->y2 + dxhw, rec->y2 - dxhw, rec->y1 - dxhw};
-    int m = 0;
+    int m = 0; /* the topmost vertex; of two at the same height the left one */
     for (int i = 1; i < 4; i++)
-        if (vy[i] < vy[m]) m = i;
+        if (vy[i] < vy[m] || (vy[i] == vy[m] && vx[i] < vx[m])) m = i;
     const int a1 = (m + 1) & 3, b1 = (m + 3) & 3, op = (m + 2) & 3;
     const int ha = vy[m] == vy[a1], hb = vy[m] == vy[b1];
-    const double sa = ha ? 0.0 : (vx[m] - vx[a1]) / (vy[m] - vy[a1]), sb = hb ? 0.0 : (vx[m] - vx[b1]) / (vy[m] - vy[b1]);
-    const int a_left = (ha || hb) ? vx[a1] < vx[b1] : sa < sb;
+    const double ta = ha ? 0.0 : (vx[m] - vx[a1]) / (vy[m] - vy[a1]), tb = hb ? 0.0 : (vx[m] - vx[b1]) / (vy[m] - vy[b1]);
+    const int a_left = (ha || hb) ? vx[a1] < vx[b1] : ta < tb;
     const int L1 = a_left ? a1 : b1, R1 = a_left ? b1 : a1;
-    const double fl = a_left ? sa : sb, fr = a_left ? sb : sa;
-    const double sl = vy[L1] == vy[op] ? 0.0 : (vx[L1] - vx[op]) / (vy[L1] - vy[op]);
-    const double sr = vy[R1] == vy[op] ? 0.0 : (vx[R1] - vx[op]) / (vy[R1] - vy[op]);
+    /* an edge that crosses no integer row counts as horizontal: its slope is taken as 0 */
+#define LSD_SLOPE(p, q) ((ceil(vy[p]) == ceil(vy[q])) ? 0.0 : (vx[p] - vx[q]) / (vy[p] - vy[q]))
+    const double fl = LSD_SLOPE(m, L1), sl = LSD_SLOPE(L1, op), fr = LSD_SLOPE(m, R1), sr = LSD_SLOPE(R1, op);
+#undef LSD_SLOPE
     const double ya_d = ceil(vy[m]), yb_d = ceil(vy[op]);
     int ya = (int)fmax(fmin(ya_d, 1e9), -1e9), yb = (int)fmax(fmin(yb_d, 1e9), -1e9);
     if (yb > s->H - 1) yb = s->H - 1;
     for (int y = ya < 0 ? 0 : ya; y <= yb; ++y) {
-        const int l2 = ((double)(y - 1) >= vy[L1]) || vy[L1] <= ya_d; /* the left limit changes edge one row late */
+        const int l2 = (double)(y - 1) >= vy[L1]; /* the left limit changes edge one row late */
         const int r2 = (double)y >= vy[R1];
         const double lx = l2 ? vx[L1] + ((double)y - vy[L1]) * sl : vx[m] + ((double)y - vy[m]) * fl;
         const double rx = r2 ? vx[R1] + ((double)y - vy[R1]) * sr : vx[m] + ((double)y - vy[m]) * fr;

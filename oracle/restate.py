@@ -171,7 +171,7 @@ def lsd_scale_image(gray, scale=0.8, sigma_scale=0.6):
 def lsd(gray, refine=0, scale=0.8, sigma_scale=0.6, quant=2.0, ang_th=22.5, log_eps=0.0, density_th=0.7,
         n_bins=1024, max_segs=1 << 16, return_debug=False, return_nfa=False):
     """-> (lines (N,1,4) f32 or None, width (N,1) f64, prec (N,1) f64[, nfa (N,1) f64 with return_nfa]).
-    refine 0 / 1 are pinned bit for bit; refine 2 (LSD_REFINE_ADV) is partially pinned (cv_restate.c)."""
+    All three refine modes are pinned bit for bit against cv2 4.13 (tests/test_oracle.py, tests/test_lsd2_oracle.py)."""
     assert refine in (0, 1, 2)
     gray = _u8(gray)
     h, w = gray.shape

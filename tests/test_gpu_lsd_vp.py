@@ -291,21 +291,26 @@ def _match_fraction(got, ref, gattr, rattr):
 
 @pytest.mark.parametrize("name", ["demo_scarce", "sc_white_2", "sc_minecraft_cave", "old_sc_inf", "sc_cube", "sc_scarce_3_flat"])
 def test_lsd_refine2_vs_oracle(engine, name, golden_inputs):
-    """LSD_REFINE_ADV: GPU against the oracle, both scales (opencv.py:142-145 runs refine 2 at .5).  A rectangle's
-    edges run exactly through the extreme pixels of its region, so the last bit of a vertex (device cos / sin
-    against glibc's) can move a pixel in or out of the NFA count: >= 97 % of the segments must match within the
-    LSD tolerance in both directions, and >= 90 % of the matched ones carry the same NFA to 1e-6.  (The oracle
-    itself is partially pinned against cv2: tests/test_lsd2_oracle.py.)"""
+    """LSD_REFINE_ADV: GPU against the oracle (which is bit-identical to cv2 in every field, tests/test_lsd2_oracle.py),
+    both scales (opencv.py:142-145 runs refine 2 at .5).  A rectangle's edges run exactly through the extreme
+    pixels of its region, so the last bit of dx / dy decides single pixels of the NFA count; with the rectangle's
+    cos / sin taken from a double-double evaluation the GPU reproduces glibc's values for 99.7 % of the angles, and
+    on these fixtures every segment and every NFA value.  The bar: >= 99 % of the segments bit-identical, all
+    within the LSD tolerance, >= 98 % of the NFA values equal to 1e-9."""
     g = R.bgr2gray(golden_inputs[name])
     for scale in (.5, .8):
         segs, width, prec, counts, nfa = engine.lsd(dev(g)[None], refine=2, scale=scale, want_nfa=True)
         ref, rw, rp, rn = R.lsd(g, 2, scale, return_nfa=True)
         n = int(counts[0])
         got, gn = segs[0, :n].cpu().numpy(), nfa[0, :n].cpu().numpy()
-        assert abs(n - len(ref)) <= max(2, 0.03 * len(ref)), (name, scale, n, len(ref))
+        assert abs(n - len(ref)) <= max(1, 0.01 * len(ref)), (name, scale, n, len(ref))
         rec, same = _match_fraction(got, ref[:, 0], gn, rn[:, 0])
         prc, _ = _match_fraction(ref[:, 0], got, rn[:, 0], gn)
-        assert rec >= 0.97 and prc >= 0.97 and same >= 0.90, (name, scale, rec, prc, same)
+        k = min(n, len(ref))
+        ident = int((got[:k] == ref[:k, 0]).all(axis=1).sum())
+        close = int((np.abs(gn[:k] - rn[:k, 0]) <= 1e-9).sum())
+        print(f"refine2 {name} {scale}: oracle {len(ref)} gpu {n} bit-identical {ident} equal-nfa {close}")
+        assert rec >= 0.99 and prc >= 0.99 and ident >= 0.99 * len(ref) and close >= 0.98 * len(ref), (name, scale)
         assert (gn > 0).all()  # log_eps = 0: every emitted segment passed the validation
     engine.check()
 
@@ -324,6 +329,6 @@ def test_lsd_refine2_through_the_shim_and_wrapper(golden_inputs):
     assert lines.ndim == 3 and lines.shape[1:] == (1, 4) and lines.dtype == np.float32
     assert nfa.shape == (len(lines), 1) and nfa.dtype == np.float64 and width.shape == prec.shape == nfa.shape
     rec, same = _match_fraction(lines[:, 0], ref[:, 0], nfa[:, 0], rn[:, 0])
-    assert rec >= 0.97 and same >= 0.90
+    assert rec >= 0.99 and same >= 0.98
     pairs = gp.detectors.lsd(img, 2, scale=0.5)
     assert len(pairs) == len(lines) and np.array_equal(np.concatenate(pairs[0]), lines[0, 0])
