@@ -147,55 +147,119 @@ __global__ void __launch_bounds__(1024, 2) k_hysteresis(u8 *__restrict__ map, u3
     const long long cap = (long long)npx - nweak;  // front may use [0, cap)
     if (nweak == 0) return;  // nothing to promote, nothing to clear (block-uniform)
     if (nweak <= 4096 && tail + nweak <= cap) {
-        // Few weak candidates (the usual case when hi is low): sweep the WEAK list instead of flooding
-        // from every strong pixel.  A weak pixel with a 255 neighbour is promoted; repeat to a fixpoint.
-        // Each thread keeps its (at most four) weak pixels in registers: a sweep is then ONE L2 round trip
-        // (the eight neighbour bytes of every live pixel, issued together) instead of three dependent ones.
-        __shared__ int s_changed, s_t2;
-        constexpr int PER = 4;  // nweak <= 4096 and the CTA has 1024 threads
+        // Few weak candidates (the usual case when hi is low): work on the WEAK list instead of flooding from every
+        // strong pixel, and keep the propagation out of global memory.  ONE round of loads fetches the eight
+        // neighbour bytes of every weak pixel (is a strong pixel adjacent?  which neighbours are weak?).  The weak
+        // pixels sit in a shared-memory hash set; their 8-connected components are formed by a union-find over the
+        // slots (atomicMin hooking, path halving), a component is promoted iff one of its pixels touches a strong
+        // one.  A constant number of barriers instead of one L2 round trip (or one shared sweep) per hop of the
+        // weak chains along a soft edge, which are hundreds of pixels long.
+        constexpr int PER = 4;          // nweak <= 4096 and the CTA has 1024 threads
+        constexpr int HS = 8192;        // hash slots (load factor <= 0.5)
+        constexpr u32 EMPTY = 0x7fffffffu, DONE = 0x80000000u;
+        extern __shared__ u32 s_dyn[];
+        u32 *s_slot = s_dyn, *s_par = s_dyn + HS;  // pixel index (bit 31: component promoted) / union-find parent
+        __shared__ int s_t2;
+        for (int i = threadIdx.x; i < HS; i += 1024) s_slot[i] = EMPTY;
+        if (threadIdx.x == 0) s_t2 = tail;
         u32 pw[PER];
-        bool live[PER];
+        u32 wm = 0;   // per pixel one byte: which of the 8 neighbours are weak
+        u32 st = 0;   // per pixel: bit k = in the list, bit 8 + k = touches a strong pixel
+        int own[PER];
 #pragma unroll
         for (int k = 0; k < PER; k++) {
             const int i = threadIdx.x + k * 1024;
-            live[k] = i < nweak;
-            pw[k] = live[k] ? q[npx - 1 - i] : 0u;
+            pw[k] = i < nweak ? q[npx - 1 - i] : 0u;
+            if (i < nweak) st |= 1u << k;
+            own[k] = 0;
         }
-        if (threadIdx.x == 0) s_t2 = tail;
-        for (;;) {
-            __syncthreads();
-            if (threadIdx.x == 0) s_changed = 0;
-            __syncthreads();
+        __syncthreads();
+        auto hsh = [](u32 p) { return (p * 2654435761u) >> 19; };  // 13 bits
 #pragma unroll
-            for (int k = 0; k < PER; k++) {  // (k >= 1 only with more than 1024 weak pixels)
-                if (!live[k]) continue;
-                const u32 p = pw[k];
-                const int y = (int)(p / (u32)w), x = (int)(p - (u32)y * w);
-                int nb[8];
+        for (int k = 0; k < PER; k++) {
+            if (!(st >> k & 1)) continue;
+            u32 hx = hsh(pw[k]);
+            while (atomicCAS(&s_slot[hx], EMPTY, pw[k]) != EMPTY) hx = (hx + 1) & (HS - 1);
+            own[k] = (int)hx;
+            s_par[hx] = hx;
+        }
 #pragma unroll
-                for (int j = 0; j < 8; j++) {
-                    const int dy = (j < 3) ? -1 : (j < 5 ? 0 : 1);
-                    const int dx = (j < 3) ? j - 1 : (j == 3 ? -1 : (j == 4 ? 1 : j - 6));
-                    const int yy = y + dy, xx = x + dx;
-                    const bool in = yy >= 0 && yy < h && xx >= 0 && xx < w;
-                    nb[j] = in ? (int)__ldcg(m + (size_t)(in ? yy : y) * w + (in ? xx : x)) : 0;
-                }
-                bool hit = false;
+        for (int k = 0; k < PER; k++) {
+            if (!(st >> k & 1)) continue;
+            const u32 p = pw[k];
+            const int y = (int)(p / (u32)w), x = (int)(p - (u32)y * w);
+            int nb[8];
 #pragma unroll
-                for (int j = 0; j < 8; j++) hit |= nb[j] == 255;
-                if (hit) {
-                    __stcg(m + p, (u8)255);  // single owner: this pixel appears once in the weak list
-                    q[atomicAdd(&s_t2, 1)] = p;
-                    s_changed = 1;
-                    live[k] = false;
+            for (int j = 0; j < 8; j++) {
+                const int dy = (j < 3) ? -1 : (j < 5 ? 0 : 1);
+                const int dx = (j < 3) ? j - 1 : (j == 3 ? -1 : (j == 4 ? 1 : j - 6));
+                const int yy = y + dy, xx = x + dx;
+                const bool in = yy >= 0 && yy < h && xx >= 0 && xx < w;
+                nb[j] = in ? (int)__ldcg(m + (size_t)(in ? yy : y) * w + (in ? xx : x)) : 0;
+            }
+            bool hit = false;
+            u32 mask = 0;
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                hit |= nb[j] == 255;
+                mask |= (nb[j] == 1 ? 1u : 0u) << j;
+            }
+            wm |= mask << (8 * k);
+            if (hit) st |= 1u << (8 + k);
+        }
+        __syncthreads();  // every weak pixel is in the set, every parent initialised
+        volatile u32 *par = s_par;
+        auto find = [&](u32 a) {
+            for (;;) {
+                const u32 pa = par[a];
+                if (pa == a) return a;
+                const u32 ga = par[pa];
+                par[a] = ga;  // path halving (benign race: parents only ever move towards the root)
+                a = ga;
+            }
+        };
+#pragma unroll
+        for (int k = 0; k < PER; k++) {
+            if (!(st >> k & 1)) continue;
+            // the four "forward" neighbours are enough: every adjacency is seen from one of its two ends
+            const u32 mask = (wm >> (8 * k)) & 0xf0u;
+            if (!mask) continue;
+            const u32 p = pw[k];
+            const int y = (int)(p / (u32)w), x = (int)(p - (u32)y * w);
+            for (u32 mm = mask; mm; mm &= mm - 1) {
+                const int j = __ffs(mm) - 1;
+                const int dy = (j < 5) ? 0 : 1;
+                const int dx = (j == 4) ? 1 : j - 6;
+                const u32 np_ = (u32)((y + dy) * w + (x + dx));
+                u32 hx = hsh(np_);
+                while ((((volatile u32 *)s_slot)[hx] & ~DONE) != np_) hx = (hx + 1) & (HS - 1);  // a weak neighbour is in the set
+                u32 a = (u32)own[k], b = hx;
+                for (;;) {  // union: hook the larger root under the smaller
+                    a = find(a);
+                    b = find(b);
+                    if (a == b) break;
+                    if (a < b) { const u32 t = a; a = b; b = t; }
+                    const u32 old = atomicMin(&s_par[a], b);
+                    if (old == a) break;
+                    a = old;
                 }
             }
-            __syncthreads();
-            if (!s_changed) break;
         }
+        __syncthreads();
 #pragma unroll
         for (int k = 0; k < PER; k++)
-            if (live[k]) __stcg(m + pw[k], (u8)0);  // weak candidates that were never reached
+            if ((st >> k & 1) && (st >> (8 + k) & 1)) atomicOr(&s_slot[find((u32)own[k])], DONE);
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < PER; k++) {
+            if (!(st >> k & 1)) continue;
+            if (((volatile u32 *)s_slot)[find((u32)own[k])] & DONE) {
+                __stcg(m + pw[k], (u8)255);
+                q[atomicAdd(&s_t2, 1)] = pw[k];
+            } else
+                __stcg(m + pw[k], (u8)0);  // weak candidates that were never reached
+        }
+        __syncthreads();
         if (threadIdx.x == 0) cnt[LE_C_QTAIL] = s_t2;
         return;
     }
@@ -387,7 +451,12 @@ int le_front_launch(le_ctx *ctx, const u8 *src, int ch, int do_blur, int do_norm
     rc = le_front_rows_launch(ctx, in, in_ch, blur, do_norm, edges, n, h, w, lo, hi, st);
     if (rc) return rc;
     LE_T0(ctx, LE_K_HYST, st);
-    k_hysteresis<<<n, 1024, 0, st>>>(edges, (u32 *)ctx->queue.p, (int *)ctx->counters.p, h, w);
+    static bool hyst_attr = false;
+    if (!hyst_attr) {
+        LE_CUDA(ctx, cudaFuncSetAttribute(k_hysteresis, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+        hyst_attr = true;
+    }
+    k_hysteresis<<<n, 1024, 65536, st>>>(edges, (u32 *)ctx->queue.p, (int *)ctx->counters.p, h, w);
     LE_T1(ctx, LE_K_HYST, st);
     LE_LAUNCH_CHECK(ctx);
     ctx->edge_list_for = edges;
