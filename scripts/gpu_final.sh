@@ -6,9 +6,9 @@ python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.log
 python bench.py > gpurun_out/bench_full.log 2>gpurun_out/bench_full.err; tail -1 gpurun_out/bench_full.log | cut -c1-1500
 python scripts/bench_others.py > gpurun_out/others.log 2>&1; tail -12 gpurun_out/others.log | cut -c1-400
 python bench.py --steps 2 --warmup 3 --no-cpu --no-e2e > gpurun_out/plain_l.log 2>&1 && \
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r1_s3_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu --no-e2e > gpurun_out/ncu_l.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r1_s4_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu --no-e2e > gpurun_out/ncu_l.log 2>&1
 tail -1 gpurun_out/ncu_l.log | cut -c1-200
 for k in k_front_rows k_hough_vote; do
-  ncu --set full --clock-control none --import-source on -k regex:$k -s 3 -c 1 -o gpurun_out/r1_s3_$k -f python bench.py --steps 2 --warmup 3 --no-cpu --no-e2e > gpurun_out/ncu_$k.log 2>&1
+  ncu --set full --clock-control none --import-source on -k regex:$k -s 3 -c 1 -o gpurun_out/r1_s4_$k -f python bench.py --steps 2 --warmup 3 --no-cpu --no-e2e > gpurun_out/ncu_$k.log 2>&1
 done
-ls -la gpurun_out/r1_s3_*
+ls -la gpurun_out/r1_s4_*
