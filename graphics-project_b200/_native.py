@@ -41,6 +41,8 @@ PROTOTYPES = {
     "le_vp_loss": (_i, [_vp, _vp, _i, _vp, _i, _d, _d, _vp, _vp]),
     "le_vp_sphere_hist": (_i, [_vp, _vp, _i, _d, _d, _vp, _i, _i, _vp]),
     "le_pair_intersections": (_i, [_vp, _vp, _i, _vp, _vp, _i, _vp]),
+    "le_polar_batch": (_i, [_vp, _vp, _vp, _i, _i, _d, _vp, _vp, _vp]),
+    "le_vp_fit_batch": (_i, [_vp, _vp, _vp, _i, _i, _d, _d, _i, _i, _i, _i, _d, _vp, _i, _i, _i, _vp, _vp]),
     "le_combine_parallel_lines": (_i, [_vp, _vp, _vp, _i, _i, _d, _d, _d, _d, _vp, _vp, _vp, _vp]),
     "le_face_quads": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _i, _i, _d, _vp, _vp, _vp, _vp, _i, _vp]),
     "le_f32_bgr2gray": (_i, [_vp, _vp, _ll, _ll, _ll, _ll, _vp, _i, _i, _i, _vp]),

@@ -305,6 +305,38 @@ class Engine:
                                            self._stream()))
         return out, count
 
+    # ------------------------------------------------------------------ a14 'lsd' branch, batched (config 5)
+    def polar_batch(self, segs, counts, min_len=10.0):
+        """LSD output of a batch (segs [N, max, 4] float32, counts [N]) -> (polar [N, max, 2] float64, pcounts [N]):
+        per frame the segments longer than ``min_len`` as (rho, phi) lines (opencv_fit_color.py:88)."""
+        segs = segs.to(self.device, torch.float32).contiguous()
+        counts = counts.to(self.device, torch.int32).contiguous()
+        n, max_segs = segs.shape[0], segs.shape[1]
+        polar = torch.empty((n, max_segs, 2), dtype=torch.float64, device=self.device)
+        pcounts = torch.empty((n,), dtype=torch.int32, device=self.device)
+        if n and max_segs:
+            self._ok(lib.le_polar_batch(self._ctx, _ptr(segs), _ptr(counts), n, max_segs, float(min_len), _ptr(polar),
+                                        _ptr(pcounts), self._stream()))
+        else:
+            pcounts.zero_()
+        return polar, pcounts
+
+    def vp_fit_batch(self, polar, pcounts, width=600.0, height=400.0, n_phi=192, n_th=96, n_ref=32, rounds=4,
+                     ref_area=0.3, n_az=360, n_el=90, top=8, want_hist=True):
+        """regress_lines for every frame of a batch in one CTA each (opencv_fit_color.py:28-47): polar
+        [N, max, 2] float64, pcounts [N] -> (fit [N, 3] float64 = (phi, theta, loss), hist [N, n_el, n_az] int32
+        or None)."""
+        polar = polar.to(self.device, torch.float64).contiguous()
+        pcounts = pcounts.to(self.device, torch.int32).contiguous()
+        n, max_lines = polar.shape[0], polar.shape[1]
+        fit = torch.empty((n, 3), dtype=torch.float64, device=self.device)
+        hist = torch.empty((n, n_el, n_az), dtype=torch.int32, device=self.device) if want_hist else None
+        self._ok(lib.le_vp_fit_batch(self._ctx, _ptr(polar), _ptr(pcounts), n, max_lines, float(width), float(height),
+                                     int(n_phi), int(n_th), int(n_ref), int(rounds), float(ref_area),
+                                     _ptr(hist) if want_hist else None, n_az, n_el, top if want_hist else 0,
+                                     _ptr(fit), self._stream()))
+        return fit, hist
+
 
     def combine_parallel_lines(self, segs, counts=None, max_distance=5, max_angle=3):
         """Batched combineParallelLines (util.py:141-159): segs [N, max_k, 4] float64 (x1,y1,x2,y2), counts [N]

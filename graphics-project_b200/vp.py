@@ -70,7 +70,7 @@ def sphere_seeds(lines, width=WIDTH, height=HEIGHT, n_az=360, n_el=90, top=8):
     hist = eng.vp_sphere_hist(torch.from_numpy(segs), width, height, n_az, n_el)
     flat = hist.flatten()
     k = min(top, flat.numel())
-    idx = torch.topk(flat, k).indices.cpu().numpy()
+    idx = torch.sort(flat, descending=True, stable=True).indices[:k].cpu().numpy()  # ties: lower bin first
     seeds = []
     for i in idx:
         be, ba = divmod(int(i), n_az)
@@ -97,8 +97,47 @@ def _grid(phi_lo, phi_hi, th_lo, th_hi, n_phi, n_th):
     return np.stack(np.meshgrid(ph, th, indexing="ij"), -1).reshape(-1, 2)
 
 
+_ROUNDS = 4
+
+
+def _search_grid(iterations, refinement_iterations):
+    """(n_phi, n_th, n_ref): grid sizes of the two search phases; the reference's draw counts are lower bounds."""
+    n_phi = max(192, int(np.ceil(np.sqrt(2 * max(iterations, 1)))))
+    return n_phi, max(96, n_phi // 2), max(32, int(np.ceil(np.sqrt(max(refinement_iterations, 1)))))
+
+
+def regress_lines_batch(polar, pcounts, iterations=500, refinement_iterations=100, refinement_area=0.3, width=WIDTH,
+                        height=HEIGHT, want_hist=True, engine=None):
+    """``regress_lines`` for every frame of a batch, one CTA per frame and no host round trip (``le_vp_fit_batch``):
+    polar [N, max, 2] float64 CUDA tensor of (rho, phi) lines, pcounts [N] -> (fit [N, 3] = (phi, theta, loss),
+    hist [N, 90, 360] Gaussian-sphere histograms or None).  Same candidates, in the same order, as
+    ``regress_lines`` evaluates step by step."""
+    eng = engine or default_engine()
+    n_phi, n_th, n_ref = _search_grid(iterations, refinement_iterations)
+    return eng.vp_fit_batch(polar, pcounts, width, height, n_phi, n_th, n_ref, _ROUNDS, float(refinement_area),
+                            want_hist=want_hist)
+
+
+def get_camera_angles_batch(frames, iterations=1000, refinement_iterations=500, width=None, height=None, max_segs=2048,
+                            engine=None):
+    """``get_camera_angles(image, method='lsd')`` (opencv_fit_color.py:71-93) for a batch of BGR frames
+    ([N, H, W, 3] uint8 CUDA tensor): gray -> LSD -> segments longer than 10 px as polar lines -> fit, all on the
+    device.  ``width`` / ``height`` default to the frame size (the reference's WIDTH / HEIGHT constants are its
+    600 x 400 image size).  Returns (fit [N, 3] = (phi, theta, loss), hist [N, 90, 360], polar, pcounts, segs,
+    counts); counts holds the true LSD segment count (> max_segs means truncated)."""
+    eng = engine or default_engine()
+    h, w = frames.shape[1], frames.shape[2]
+    gray = eng.bgr2gray(frames)
+    segs, _, _, counts = eng.lsd(gray, max_segs=max_segs)
+    polar, pcounts = eng.polar_batch(segs, counts, 10.0)
+    fit, hist = regress_lines_batch(polar, pcounts, iterations, refinement_iterations, 0.3,
+                                    float(w if width is None else width), float(h if height is None else height),
+                                    engine=eng)
+    return fit, hist, polar, pcounts, segs, counts
+
+
 def regress_lines(lines, iterations=500, refinement_iterations=100, refinement_area=0.3, width=WIDTH,
-                  height=HEIGHT, verbose=True):
+                  height=HEIGHT, verbose=True, use_seeds=True):
     """opencv_fit_color.py:28-47 signature and return type; deterministic GPU search.
 
     ``iterations`` / ``refinement_iterations`` are lower bounds on the number of candidates per phase."""
@@ -107,9 +146,9 @@ def regress_lines(lines, iterations=500, refinement_iterations=100, refinement_a
     best = (0, 0)
     if len(lines) == 0:
         raise ZeroDivisionError("division by zero")  # min_loss divides by len(lines) in the reference
-    n_phi = max(192, int(np.ceil(np.sqrt(2 * max(iterations, 1)))))
-    cand = _grid(0, np.pi, 0, np.pi / 2, n_phi, max(96, n_phi // 2))
-    seeds = sphere_seeds(lines, width, height)
+    n_phi, n_th, n_ref = _search_grid(iterations, refinement_iterations)
+    cand = _grid(0, np.pi, 0, np.pi / 2, n_phi, n_th)
+    seeds = sphere_seeds(lines, width, height) if use_seeds else []
     if len(seeds):
         cand = np.concatenate([cand, seeds])
     ls = losses(lines, cand, width, height)
@@ -118,8 +157,7 @@ def regress_lines(lines, iterations=500, refinement_iterations=100, refinement_a
     if ls[i] < best_loss:
         best_loss, best = float(ls[i]), (float(cand[i, 0]), float(cand[i, 1]))
     side = float(refinement_area)
-    n_ref = max(32, int(np.ceil(np.sqrt(max(refinement_iterations, 1)))))
-    for _ in range(4):  # reference does one refinement pass; extra passes only shrink the box
+    for _ in range(_ROUNDS):  # reference does one refinement pass; extra passes only shrink the box
         cphi, cth = best
         cand = _grid(cphi - side / 2, cphi + side / 2, cth - side / 2, cth + side / 2, n_ref, n_ref)
         ls = losses(lines, cand, width, height)

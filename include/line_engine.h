@@ -144,6 +144,28 @@ int le_vp_sphere_hist(le_ctx *ctx, const double *segs, int m, double width, doub
 int le_pair_intersections(le_ctx *ctx, const float *lines, int m, double *out, int32_t *count, int max_out,
                           void *stream);
 
+/* ---- a14 ('lsd' branch) for a whole batch; BASELINE config 5 (--pipeline lines: LSD segments + vanishing-point
+ *      Gaussian-sphere voting).  Replaces, for n frames at once and without a host round trip:
+ *      the list comprehension of get_camera_angles                opencv_fit_color.py:88-89
+ *      (keep ||b - a|| > min_len, then edges_to_polar_lines       opencv_renewed.py:16-17)
+ * segs: float32 [n][max_segs][4] and counts: int32 [n] exactly as le_lsd writes them (16-byte aligned).
+ * polar: float64 [n][max_segs][2] (rho, phi), kept lines in segment order; pcounts: int32 [n].          */
+int le_polar_batch(le_ctx *ctx, const float *segs, const int32_t *counts, int n, int max_segs, double min_len,
+                   double *polar, int32_t *pcounts, void *stream);
+
+/*      and regress_lines(lines, iterations, refinement_iterations, refinement_area)   opencv_fit_color.py:28-47
+ *      per frame, seeded by the frame's Gaussian-sphere histogram (le_vp_sphere_hist of the lines drawn through
+ *      the image).  One CTA per frame evaluates sum_loss (:14-26) for every candidate:
+ *      phase 1 = n_phi x n_th grid over [0,pi) x [0,pi/2) + the seeds of the `top` (<= 16) highest histogram
+ *      bins; phase 2 = `rounds` grids of n_ref x n_ref around the best so far, the first of side ref_area,
+ *      each next one 4/n_ref of the last; a later candidate replaces the best only if strictly lower.
+ * polar: float64 [n][max_lines][2]; pcounts: int32 [n]; hist: int32 [n][n_el][n_az] (written) or NULL (no
+ * seeds); fit: float64 [n][3] = (phi, theta, loss); a frame with no lines gives (0, 0, 100000), the reference's
+ * initial best.                                                                                         */
+int le_vp_fit_batch(le_ctx *ctx, const double *polar, const int32_t *pcounts, int n, int max_lines, double width,
+                    double height, int n_phi, int n_th, int n_ref, int rounds, double ref_area, int32_t *hist,
+                    int n_az, int n_el, int top, double *fit, void *stream);
+
 /* ---- n2  replaces: combineParallelLines(lines, max_distance=5, max_angle=3)   util.py:141-159
  *      (with combineEdges util.py:115-139, edgeDistance :103-108, getEdgeProjection :27-52; callers
  *      opencv.py:225 linesToPlanarGraph, graph.py:116 makeGraphFromLines, opencv_renewed.py:56-60 smoothEdges)
