@@ -78,3 +78,29 @@ def canny_hough_sharded(engine, frames_local, total, lo, hi, rho, theta, thresho
     engine.front_canny(frames_local, lo, hi, blur=blur)
     lines, _, counts, _ = engine.hough_lines(None, rho, theta, threshold, max_lines=max_lines, want_votes=False)
     return gather_results(counts, lines, total, group)
+
+
+def gather_vp(pcounts, fit, hist, total, group=None, scene_hist=False):
+    """Gather the `lines` pipeline's per-frame results: ``pcounts`` [b] with ``fit``
+    [b, 3] = (phi, theta, loss), and the Gaussian-sphere histograms ``hist`` [b, n_el, n_az].  With
+    ``scene_hist`` the histograms are summed over every frame of the batch instead (one ``all_reduce`` of
+    [n_el, n_az]: frames of one scene share their vanishing points).  Returns (pcounts [total], fit [total, 3],
+    hist [total, n_el, n_az] or [n_el, n_az]) on every rank."""
+    all_counts, all_fit = gather_results(pcounts, fit, total, group, slot="vp_fit")
+    if scene_hist:
+        scene = hist.sum(0)
+        if dist.get_world_size(group) > 1:
+            dist.all_reduce(scene, group=group)
+        return all_counts, all_fit, scene
+    _, all_hist = gather_results(pcounts, hist, total, group, slot="vp_hist")
+    return all_counts, all_fit, all_hist
+
+
+def lines_vp_sharded(engine, frames_local, total, iterations=1000, refinement_iterations=500, max_segs=2048,
+                     group=None, scene_hist=False):
+    """BASELINE config 5 on this rank's frames (gray -> LSD -> polar lines -> sphere histogram -> fit), then the
+    gather of (pcounts, fit, histograms) of the whole batch."""
+    from . import vp
+    fit, hist, _, pcounts, _, _ = vp.get_camera_angles_batch(frames_local, iterations, refinement_iterations,
+                                                             max_segs=max_segs, engine=engine)
+    return gather_vp(pcounts, fit, hist, total, group, scene_hist)

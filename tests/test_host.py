@@ -51,6 +51,44 @@ def _gather_worker(rank, world, port, total, q):
     dist.destroy_process_group()
 
 
+def _gather_vp_worker(rank, world, port, total, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    lo, hi = gdist.shard_range(total, rank, world)
+    ids = torch.arange(lo, hi)
+    pcounts = (ids % 4).to(torch.int32)
+    fit = torch.stack([ids * 0.5, ids * 0.25, ids + 100.0], 1).to(torch.float64)
+    hist = torch.zeros((hi - lo, 3, 5), dtype=torch.int32)
+    hist[:, 1, 2] = ids.to(torch.int32) + 1
+    c, f, h = gdist.gather_vp(pcounts, fit, hist, total)
+    c2, f2, scene = gdist.gather_vp(pcounts, fit, hist, total, scene_hist=True)
+    assert torch.equal(c, c2) and torch.equal(f, f2)
+    q.put((rank, c.numpy().copy(), f.numpy().copy(), h.numpy().copy(), scene.numpy().copy()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("total", [5, 6])
+def test_gather_vp_gloo_world2(total):
+    """(pcounts, fit, sphere histograms) of the lines pipeline: per-frame gather and the scene-level reduce."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gather_vp_worker, args=(r, 2, port, total, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    ids = np.arange(total)
+    for _, c, f, h, scene in got:
+        assert np.array_equal(c, ids % 4)
+        assert np.array_equal(f, np.stack([ids * 0.5, ids * 0.25, ids + 100.0], 1))
+        assert h.shape == (total, 3, 5) and np.array_equal(h[:, 1, 2], ids + 1) and h.sum() == (ids + 1).sum()
+        assert scene.shape == (3, 5) and scene[1, 2] == (ids + 1).sum() and scene.sum() == (ids + 1).sum()
+
+
 @pytest.mark.parametrize("total", [7, 8])
 def test_gather_results_gloo_world2(total):
     ctx = mp.get_context("spawn")
