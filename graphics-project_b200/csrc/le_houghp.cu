@@ -38,6 +38,96 @@ __global__ void __launch_bounds__(256) k_nz_count(const u8 *__restrict__ edges, 
     }
 }
 // pass 2: ordered (row-major) write of packed (y<<16|x) + mask bytes
+// The same two passes with 16 pixels per thread (one 16-byte load, __vsetne4 gives the mask bytes and, by popc,
+// the count): for frames whose size is a multiple of 16 bytes (1080p, 4K, 600 x 400).  Same list, same mask.
+__global__ void __launch_bounds__(256) k_nz_count16(const u8 *__restrict__ edges, int *__restrict__ segcnt, size_t npx,
+                                                    int nseg)
+{
+    const int f = blockIdx.y, s = blockIdx.x;
+    const uint4 *e = (const uint4 *)(edges + (size_t)f * npx);
+    const size_t v0 = (size_t)s * (NZ_SEG / 16), v1 = min(npx / 16, v0 + NZ_SEG / 16);
+    int c = 0;
+    for (size_t i = v0 + threadIdx.x; i < v1; i += 256) {
+        const uint4 v = e[i];
+        c += __popc(__vsetne4(v.x, 0)) + __popc(__vsetne4(v.y, 0)) + __popc(__vsetne4(v.z, 0)) + __popc(__vsetne4(v.w, 0));
+    }
+    __shared__ int red[8];
+    for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(~0u, c, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int k = 0; k < 8; k++) t += red[k];
+        segcnt[f * nseg + s] = t;
+    }
+}
+__global__ void __launch_bounds__(256) k_nz_write16(const u8 *__restrict__ edges, const int *__restrict__ segcnt,
+                                                    u32 *__restrict__ nz, u8 *__restrict__ mask,
+                                                    int *__restrict__ counters, size_t npx, int nseg, int w)
+{
+    const int f = blockIdx.y, s = blockIdx.x;
+    const uint4 *e = (const uint4 *)(edges + (size_t)f * npx);
+    uint4 *mk = (uint4 *)(mask + (size_t)f * npx);
+    u32 *out = nz + (size_t)f * npx;
+    __shared__ int s_base, warp_off[8];
+    int part = 0;  // exclusive prefix of the segment counts
+    for (int k = threadIdx.x; k < s; k += 256) part += segcnt[f * nseg + k];
+    for (int o = 16; o; o >>= 1) part += __shfl_xor_sync(~0u, part, o);
+    if ((threadIdx.x & 31) == 0) warp_off[threadIdx.x >> 5] = part;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int k = 0; k < 8; k++) t += warp_off[k];
+        s_base = t;
+        if (s == nseg - 1) counters[f * LE_C_STRIDE + LE_C_AUX0] = t + segcnt[f * nseg + s];
+    }
+    __syncthreads();
+    int base = s_base;
+    const size_t v0 = (size_t)s * (NZ_SEG / 16), v1 = min(npx / 16, v0 + NZ_SEG / 16);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (size_t c0 = v0; c0 < v1; c0 += 256) {
+        const size_t i = c0 + threadIdx.x;
+        u32 m[4] = {0, 0, 0, 0};
+        if (i < v1) {
+            const uint4 v = e[i];
+            m[0] = __vsetne4(v.x, 0); m[1] = __vsetne4(v.y, 0); m[2] = __vsetne4(v.z, 0); m[3] = __vsetne4(v.w, 0);
+            mk[i] = make_uint4(m[0], m[1], m[2], m[3]);
+        }
+        const int cnt = __popc(m[0]) + __popc(m[1]) + __popc(m[2]) + __popc(m[3]);
+        int inc = cnt;  // inclusive warp scan
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(~0u, inc, o);
+            if (lane >= o) inc += t;
+        }
+        __syncthreads();
+        if (lane == 31) warp_off[wid] = inc;
+        __syncthreads();
+        int off = 0, tot = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            if (k < wid) off += warp_off[k];
+            tot += warp_off[k];
+        }
+        if (cnt) {
+            int pos = base + off + inc - cnt;
+            const size_t p0 = i * 16;
+            const int y = (int)(p0 / w), x = (int)(p0 - (size_t)y * w);
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                if (!m[j]) continue;
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    if (m[j] >> (8 * k) & 1) {
+                        int xx = x + 4 * j + k, yy = y;
+                        while (xx >= w) { xx -= w; yy++; }
+                        out[pos++] = ((u32)yy << 16) | (u32)xx;
+                    }
+            }
+        }
+        base += tot;
+    }
+}
 __global__ void __launch_bounds__(256) k_nz_write(const u8 *__restrict__ edges, const int *__restrict__ segcnt,
                                                   u32 *__restrict__ nz, u8 *__restrict__ mask,
                                                   int *__restrict__ counters, size_t npx, int nseg, int w)
@@ -341,10 +431,17 @@ extern "C" int le_hough_lines_p(le_ctx *ctx, const uint8_t *edges, int n, int h,
     ctx->edge_list_for = nullptr;  // AUX counters are ours now; the edge lists stay valid but keep it simple
     int *segcnt = (int *)((char *)ctx->misc.p + 256);
     LE_T0(ctx, LE_K_PPHT_PREP, st);
-    k_nz_count<<<dim3(nseg, n), 256, 0, st>>>(edges, segcnt, npx, nseg);
-    LE_LAUNCH_CHECK(ctx);
-    k_nz_write<<<dim3(nseg, n), 256, 0, st>>>(edges, segcnt, (u32 *)ctx->ppht_nz.p, (u8 *)ctx->ppht_mask.p,
-                                              (int *)ctx->counters.p, npx, nseg, w);
+    if ((npx & 15) == 0 && ((size_t)edges & 15) == 0) {  // 16 pixels per thread
+        k_nz_count16<<<dim3(nseg, n), 256, 0, st>>>(edges, segcnt, npx, nseg);
+        LE_LAUNCH_CHECK(ctx);
+        k_nz_write16<<<dim3(nseg, n), 256, 0, st>>>(edges, segcnt, (u32 *)ctx->ppht_nz.p, (u8 *)ctx->ppht_mask.p,
+                                                    (int *)ctx->counters.p, npx, nseg, w);
+    } else {
+        k_nz_count<<<dim3(nseg, n), 256, 0, st>>>(edges, segcnt, npx, nseg);
+        LE_LAUNCH_CHECK(ctx);
+        k_nz_write<<<dim3(nseg, n), 256, 0, st>>>(edges, segcnt, (u32 *)ctx->ppht_nz.p, (u8 *)ctx->ppht_mask.p,
+                                                  (int *)ctx->counters.p, npx, nseg, w);
+    }
     LE_LAUNCH_CHECK(ctx);
     if (numangle <= 192 && !getenv("LE_PPHT_GENERIC"))  // batched kernel (le_houghp_fast.cu); same results
         return le_ppht_fast_launch(ctx, n, h, w, numangle, stride, threshold, min_line_length, max_line_gap, segs,

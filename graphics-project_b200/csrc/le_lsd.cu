@@ -145,6 +145,86 @@ __global__ void __launch_bounds__(256) k_resize_exact(const u8 *__restrict__ src
     d[(size_t)y * dw + x] = (u8)((v + 32768u) >> 16);
 }
 
+// ------------------------------------------------------------------ 1a' + 1b fused: blur tile -> resize
+// One CTA produces a dtw x dth tile of the down-scaled image: it stages the source words its samples need
+// (+ the blur halo), runs the two blur passes of k_sepblur_q8_w into a shared 128 x 32 tile of blurred bytes
+// and samples that tile with the exact bilinear weights -- the full-resolution blurred image (one write and one
+// read of W*H bytes per frame) never exists.  The host picks dtw / dth so that every tile's samples fit the
+// shared tile (checked against the tables).  Same integer arithmetic as the two kernels: same bytes.
+template <int R>
+__global__ void __launch_bounds__(256) k_blur_resize_w(const u8 *__restrict__ src, int h, int w, u8 *__restrict__ dst,
+                                                       int dh, int dw, int dth, int dtw, const int *__restrict__ taps,
+                                                       const int2 *__restrict__ xtab, const int2 *__restrict__ ytab)
+{
+    __shared__ u32 raw[SV_TH + 2 * R][SV_CW];
+    __shared__ __align__(8) u32 vb[SV_TH][SV_CW][2];  // column sums, u16 x 4 per staged word
+    __shared__ u32 bl[SV_TH][SV_TW / 4];              // blurred bytes
+    __shared__ int tp[2 * R + 1];
+    const u8 *s = src + (size_t)blockIdx.z * h * w;
+    u8 *d = dst + (size_t)blockIdx.z * dh * dw;
+    const int dx0 = blockIdx.x * dtw, dy0 = blockIdx.y * dth;
+    const int tw = min(dtw, dw - dx0), th = min(dth, dh - dy0);
+    const int x0 = xtab[dx0].x & ~3, y0 = ytab[dy0].x;  // source origin of the shared tile
+    if (threadIdx.x < 2 * R + 1) tp[threadIdx.x] = taps[threadIdx.x];
+    const bool interior = x0 >= 8 && x0 + SV_TW + 8 <= w;
+    for (int i = threadIdx.x; i < (SV_TH + 2 * R) * SV_CW; i += 256) {
+        const int ty = i / SV_CW, c = i - ty * SV_CW;
+        const u8 *row = s + (size_t)d_reflect101(y0 + ty - R, h) * w;
+        const int xb = x0 - 8 + 4 * c;
+        u32 v;
+        if (interior) v = *(const u32 *)(row + xb);
+        else {
+            v = 0;
+#pragma unroll
+            for (int k = 0; k < 4; k++) v |= (u32)row[d_reflect101(min(xb + k, 2 * w - 2), w)] << (8 * k);
+        }
+        raw[ty][c] = v;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < SV_TH * SV_CW; i += 256) {
+        const int ty = i / SV_CW, c = i - ty * SV_CW;
+        u32 a01 = 0, a23 = 0;
+#pragma unroll
+        for (int t = 0; t <= 2 * R; t++) {
+            const u32 wd = raw[ty + t][c];
+            a01 += (u32)tp[t] * __byte_perm(wd, 0, 0x4140);
+            a23 += (u32)tp[t] * __byte_perm(wd, 0, 0x4342);
+        }
+        *(uint2 *)vb[ty][c] = make_uint2(a01, a23);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < SV_TH * (SV_TW / 4); i += 256) {
+        const int ty = i / (SV_TW / 4), oc = i - ty * (SV_TW / 4);
+        const u16 *v16 = (const u16 *)vb[ty] + 8 + 4 * oc - R;  // column sum of pixel x0 + 4 oc - R
+        u32 vv[4 + 2 * R];
+#pragma unroll
+        for (int j = 0; j < 4 + 2 * R; j++) vv[j] = v16[j];
+        u32 out = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            u32 acc = 0;
+#pragma unroll
+            for (int t = 0; t <= 2 * R; t++) acc += (u32)tp[t] * vv[k + t];
+            out |= ((acc + 32768u) >> 16) << (8 * k);
+        }
+        bl[ty][oc] = out;
+    }
+    __syncthreads();
+    const u8 *b8 = (const u8 *)bl;
+    for (int yy = threadIdx.x >> 5; yy < th; yy += 8) {
+        const int2 yt = ytab[dy0 + yy];
+        const int r0 = (yt.x - y0) * SV_TW, r1 = (min(yt.x + 1, h - 1) - y0) * SV_TW;
+        for (int xx = threadIdx.x & 31; xx < tw; xx += 32) {
+            const int2 xt = xtab[dx0 + xx];
+            const int c0 = xt.x - x0, c1 = min(xt.x + 1, w - 1) - x0;
+            const u32 a = (u32)(256 - xt.y) * b8[r0 + c0] + (u32)xt.y * b8[r0 + c1];
+            const u32 b = (u32)(256 - xt.y) * b8[r1 + c0] + (u32)xt.y * b8[r1 + c1];
+            const u32 v = (u32)(256 - yt.y) * a + (u32)yt.y * b;
+            d[(size_t)(dy0 + yy) * dw + dx0 + xx] = (u8)((v + 32768u) >> 16);
+        }
+    }
+}
+
 // ------------------------------------------------------------------ 2: gradient / level-line angle
 static __device__ __forceinline__ float d_fast_atan2(float y, float x)
 {
@@ -1412,7 +1492,23 @@ extern "C" int le_lsd(le_ctx *ctx, const uint8_t *gray, int n, int h, int w, int
         resize_tab(h, H, scale, yt);
         size_t tab_bytes = 128 + sizeof(int2) * ((size_t)W + H);
         if ((rc = le_ensure(ctx, &ctx->lsd_tab, tab_bytes))) return rc;
-        if ((rc = le_ensure(ctx, &ctx->lsd0, (size_t)h * w * n))) return rc;  // blurred full-res
+        const bool wordwise = (w & 3) == 0 && (((size_t)gray) & 3) == 0 && (hh == 3 || hh == 5);
+        // fused blur + resize: the largest destination tile whose samples fit the 128 x 32 shared tile
+        int dtw = 0, dth = 0;
+        static const int unfused = getenv("LE_LSD_UNFUSED") ? 1 : 0;  // development knob: the two-kernel path
+        if (wordwise && scale < 1 && !unfused) {
+            auto fits = [](const std::vector<int2> &tab, int src, int dt, int cap, int align) {
+                for (int d0 = 0; d0 < (int)tab.size(); d0 += dt) {
+                    const int last = std::min(d0 + dt, (int)tab.size()) - 1;
+                    if (std::min(tab[last].x + 1, src - 1) - (tab[d0].x & ~align) >= cap) return false;
+                }
+                return true;
+            };
+            for (dtw = std::min(W, (int)((SV_TW - 5) * scale)); dtw >= 16 && !fits(xt, w, dtw, SV_TW, 3); dtw--) {}
+            for (dth = std::min(H, (int)((SV_TH - 2) * scale)); dth >= 4 && !fits(yt, h, dth, SV_TH, 0); dth--) {}
+            if (dtw < 16 || dth < 4) dtw = dth = 0;
+        }
+        if (!dtw && (rc = le_ensure(ctx, &ctx->lsd0, (size_t)h * w * n))) return rc;  // blurred full-res
         char *tb = (char *)ctx->lsd_tab.p;
         if (!(ctx->lsd_key[0] == h && ctx->lsd_key[1] == w && ctx->lsd_key[2] == scale && ctx->lsd_key[3] == sigma_scale)) {
             // pageable-source copies are staged before cudaMemcpyAsync returns
@@ -1421,9 +1517,15 @@ extern "C" int le_lsd(le_ctx *ctx, const uint8_t *gray, int n, int h, int w, int
             LE_CUDA(ctx, cudaMemcpyAsync(tb + 128 + sizeof(int2) * W, yt.data(), sizeof(int2) * H, cudaMemcpyHostToDevice, st));
             ctx->lsd_key[0] = h; ctx->lsd_key[1] = w; ctx->lsd_key[2] = scale; ctx->lsd_key[3] = sigma_scale;
         }
-        const bool wordwise = (w & 3) == 0 && (((size_t)gray) & 3) == 0 && (hh == 3 || hh == 5);
         const dim3 gw((w + SV_TW - 1) / SV_TW, (h + SV_TH - 1) / SV_TH, n);
-        if (wordwise && hh == 3)
+        const int2 *xtd = (const int2 *)(tb + 128), *ytd = (const int2 *)(tb + 128 + sizeof(int2) * W);
+        if (dtw) {
+            const dim3 gf((W + dtw - 1) / dtw, (H + dth - 1) / dth, n);
+            if (hh == 3)
+                k_blur_resize_w<3><<<gf, 256, 0, st>>>(gray, h, w, (u8 *)ctx->lsd1.p, H, W, dth, dtw, (const int *)tb, xtd, ytd);
+            else
+                k_blur_resize_w<5><<<gf, 256, 0, st>>>(gray, h, w, (u8 *)ctx->lsd1.p, H, W, dth, dtw, (const int *)tb, xtd, ytd);
+        } else if (wordwise && hh == 3)
             k_sepblur_q8_w<3><<<gw, 256, 0, st>>>(gray, (u8 *)ctx->lsd0.p, h, w, (const int *)tb);
         else if (wordwise)
             k_sepblur_q8_w<5><<<gw, 256, 0, st>>>(gray, (u8 *)ctx->lsd0.p, h, w, (const int *)tb);
@@ -1431,10 +1533,11 @@ extern "C" int le_lsd(le_ctx *ctx, const uint8_t *gray, int n, int h, int w, int
             k_sepblur_q8<<<dim3((w + SB_TW - 1) / SB_TW, (h + SB_TH - 1) / SB_TH, n), 256, 0, st>>>(
                 gray, (u8 *)ctx->lsd0.p, h, w, (const int *)tb, (int)hh);
         LE_LAUNCH_CHECK(ctx);
-        k_resize_exact<<<dim3((W + 31) / 32, (H + 7) / 8, n), 256, 0, st>>>(
-            (const u8 *)ctx->lsd0.p, h, w, (u8 *)ctx->lsd1.p, H, W, (const int2 *)(tb + 128),
-            (const int2 *)(tb + 128 + sizeof(int2) * W));
-        LE_LAUNCH_CHECK(ctx);
+        if (!dtw) {
+            k_resize_exact<<<dim3((W + 31) / 32, (H + 7) / 8, n), 256, 0, st>>>((const u8 *)ctx->lsd0.p, h, w,
+                                                                                (u8 *)ctx->lsd1.p, H, W, xtd, ytd);
+            LE_LAUNCH_CHECK(ctx);
+        }
         img = (const u8 *)ctx->lsd1.p;
     }
     LsdParams P;

@@ -242,14 +242,16 @@ def test_lsd_speculative_equals_sequential_kernel():
         "            h.update(segs[i, :c[i]].cpu().numpy().tobytes()); h.update(width[i, :c[i]].cpu().numpy().tobytes())\n"
         "eng.check(); print('LSDHASH', h.hexdigest(), int(c.sum()))\n" % root)
     outs = []
-    for env in ({"LE_LSD_SERIAL": "1"}, {"LE_LSD_K": "16"}, {"LE_LSD_K": "8"}):
+    # LE_LSD_UNFUSED: separate blur and resize kernels instead of the fused tile kernel -- same bytes
+    for env in ({"LE_LSD_SERIAL": "1"}, {"LE_LSD_K": "16"}, {"LE_LSD_K": "8"}, {"LE_LSD_UNFUSED": "1"}):
         e = dict(os.environ)
         e.pop("LE_LSD_SERIAL", None)
+        e.pop("LE_LSD_UNFUSED", None)
         e.update(env)
         r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=e, timeout=600)
         assert r.returncode == 0, r.stderr[-2000:]
         outs.append([l for l in r.stdout.splitlines() if l.startswith("LSDHASH")][0])
-    assert outs[0] == outs[1] == outs[2], outs
+    assert outs[0] == outs[1] == outs[2] == outs[3], outs
 
 
 def test_lsd_repeatable_under_speculation(engine):
