@@ -86,8 +86,20 @@ int le_hough_upload_trig(le_ctx *ctx, int kind, int h, int w, double rho, double
     return LE_OK;
 }
 
-#define HV_THREADS 1024
-#define HV_ZERO_WORDS 1024
+// CTA shape of the vote kernel (overridable for development builds, scripts/vote_shape.sh)
+// Measured at 256 x 1080p (stripe histogram 70.7 KB): 1024 threads x 2 CTAs per SM 0.396 ms, 512 x 2 0.412,
+// 768 x 2 0.392, 384 x 3 0.399, 448 x 3 0.389, 512 x 3 0.373, 576 x 3 0.376, 608 x 3 0.369, 640 x 3 0.372, 512 x 4
+// with 8-angle stripes 0.383: what counts is the third resident CTA (its vote phase overlaps the write-out of the
+// other two); 512 x 3 leaves 2.8 KB of shared-memory slack.
+#ifndef HV_THREADS
+#define HV_THREADS 512
+#endif
+#ifndef HV_ZERO_WORDS
+#define HV_ZERO_WORDS 256
+#endif
+#ifndef HV_MINB
+#define HV_MINB 3  // resident CTAs per SM the stripe height is chosen for
+#endif
 #define HV_CAND_CAP 8192   // per-frame list of peak candidates on stripe-boundary rows
 
 // Shared histogram of a stripe: u16 counters, two ANGLE ROWS per 32-bit word, bin-major:
@@ -146,7 +158,7 @@ static __device__ void sort_frame(const u64 *pk, int total, int peak_cap, int nu
 // the peaks) makes the one missing comparison from the global accumulator (L2) -- a few hundred loads per
 // frame.  That needs the accumulator output, so HALO is kept for accum == NULL.
 template <int A, bool HALO>
-__global__ void __launch_bounds__(HV_THREADS, (A <= 16 ? 2 : 1))
+__global__ void __launch_bounds__(HV_THREADS, (A <= 16 ? HV_MINB : 1))
 k_hough_vote(const u32 *__restrict__ queue, int *__restrict__ counters, const float *__restrict__ trig,
              int32_t *__restrict__ accum, u64 *__restrict__ peaks, int peak_cap, int h, int w, int numangle,
              int numrho, int stride, int threshold, float rho, float theta, float *__restrict__ lines,
@@ -477,9 +489,9 @@ extern "C" int le_hough_lines(le_ctx *ctx, const uint8_t *edges, int n, int h, i
     k_zero_peaks<<<(n + 255) / 256, 256, 0, st>>>((int *)ctx->counters.p, n);
     LE_LAUNCH_CHECK(ctx);
     size_t budget = (size_t)ctx->smem_optin - 1024 - sizeof(float2) * HV_THREADS - 4 * HV_ZERO_WORDS;
-    // angles per CTA: the largest stripe whose counters leave room for two resident CTAs per SM (their
+    // angles per CTA: the largest stripe whose counters leave room for HV_MINB resident CTAs per SM (their
     // zero / vote / write phases then overlap); fall back to whatever fits one CTA
-    size_t two = budget / 2 - 4096;
+    size_t two = budget / HV_MINB - 4096;
     int A = 0;
     for (int cand = 32; cand >= 8 && !A; cand >>= 1)
         if ((size_t)cand * stride * 2 <= two) A = cand;
