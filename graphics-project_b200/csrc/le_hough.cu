@@ -231,42 +231,8 @@ k_hough_vote(const u32 *__restrict__ queue, int *__restrict__ counters, const fl
         asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(sa), "r"(on ? inc : 0u) : "memory");
     };
     __syncthreads();
-    for (int base = warp * 32; base < nedge; base += nwarps * 32) {
-        // each lane converts one queue entry to float (x, y) and stages it; the warp then votes the
-        // 32 pixels, two per broadcast LDS.128 (lanes = angles, so no two lanes share a row)
-        int idx = base + lane;
-        int p = idx < nedge ? (int)q[idx] : 0;
-        int py = (int)((float)p * rw);  // estimate of p / w, then exact correction
-        int px = p - py * w;
-        if (small) {  // p < 2^24 is exact in float and the estimate is off by one at most: two selects, no loop
-            if (px < 0) { px += w; py--; }
-            if (px >= w) { px -= w; py++; }
-        } else {
-            while (px < 0) { px += w; py--; }
-            while (px >= w) { px -= w; py++; }
-        }
-        __syncwarp();
-        s_stage[warp][lane] = make_float2((float)px, (float)py);
-        __syncwarp();
-        const int cntw = min(32, nedge - base);
-        if (cntw == 32) {
-#pragma unroll 4
-            for (int i = 0; i < 16; i += PPW) {
-                const float4 xy = stage[i + sub];
-                vote(xy.x, xy.y, true);
-                vote(xy.z, xy.w, true);
-            }
-        } else {
-            for (int i = 0; i < 16; i += PPW) {
-                const float4 xy = stage[i + sub];
-                vote(xy.x, xy.y, 2 * (i + sub) < cntw);
-                vote(xy.z, xy.w, 2 * (i + sub) + 1 < cntw);
-            }
-        }
-    }
-    __syncthreads();
-
-    // ---- write the stripe's accumulator rows + peak test
+    // ---- accumulator rows of the stripe; the zeros outside the supports do not depend on the votes: they are
+    // handed to the copy engine BEFORE the vote loop, so 63 % of the stripe's HBM writes run beside the voting
     int32_t *acc_f = accum ? accum + (size_t)f * asz : nullptr;
     u64 *pk = peaks + (size_t)f * peak_cap;
     const int n_last = min(n_first + OUT, numangle);  // exclusive
@@ -305,6 +271,42 @@ k_hough_vote(const u32 *__restrict__ queue, int *__restrict__ counters, const fl
         }
         if (issued) asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     }
+    for (int base = warp * 32; base < nedge; base += nwarps * 32) {
+        // each lane converts one queue entry to float (x, y) and stages it; the warp then votes the
+        // 32 pixels, two per broadcast LDS.128 (lanes = angles, so no two lanes share a row)
+        int idx = base + lane;
+        int p = idx < nedge ? (int)q[idx] : 0;
+        int py = (int)((float)p * rw);  // estimate of p / w, then exact correction
+        int px = p - py * w;
+        if (small) {  // p < 2^24 is exact in float and the estimate is off by one at most: two selects, no loop
+            if (px < 0) { px += w; py--; }
+            if (px >= w) { px -= w; py++; }
+        } else {
+            while (px < 0) { px += w; py--; }
+            while (px >= w) { px -= w; py++; }
+        }
+        __syncwarp();
+        s_stage[warp][lane] = make_float2((float)px, (float)py);
+        __syncwarp();
+        const int cntw = min(32, nedge - base);
+        if (cntw == 32) {
+#pragma unroll 4
+            for (int i = 0; i < 16; i += PPW) {
+                const float4 xy = stage[i + sub];
+                vote(xy.x, xy.y, true);
+                vote(xy.z, xy.w, true);
+            }
+        } else {
+            for (int i = 0; i < 16; i += PPW) {
+                const float4 xy = stage[i + sub];
+                vote(xy.x, xy.y, 2 * (i + sub) < cntw);
+                vote(xy.z, xy.w, 2 * (i + sub) + 1 < cntw);
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- write the supports of the stripe's accumulator rows + peak test
     // (2) the supports: lane = (row a, slot sub); a warp step covers 4 * PPW bins of every row of the
     // stripe -- each lane gathers four consecutive bins of ITS row and stores 16 bytes to ITS global row
     // (the row origin was shifted so that this store is aligned); peaks are tested from shared memory
