@@ -16,6 +16,7 @@
 #include "le_common.cuh"
 #include <vector>
 #include <stdlib.h>
+#include <cuda_fp16.h>
 
 static void hough_dims_host(int h, int w, double rho, double theta, int *numangle, int *numrho)
 {
@@ -157,7 +158,9 @@ static __device__ void sort_frame(const u64 *pk, int total, int peak_cap, int nu
 // shared memory go to a per-frame candidate list, and the last CTA of the frame to finish (which also orders
 // the peaks) makes the one missing comparison from the global accumulator (L2) -- a few hundred loads per
 // frame.  That needs the accumulator output, so HALO is kept for accum == NULL.
-template <int A, bool HALO>
+// H16: frames up to 2048 x 2048 stage a pixel as a half2 (integers below 2049 are exact in fp16): one LDS.128
+// then carries FOUR pixels to a half-warp instead of two -- half the staging wavefronts on the LSU data pipe.
+template <int A, bool HALO, bool H16>
 __global__ void __launch_bounds__(HV_THREADS, (A <= 16 ? HV_MINB : 1))
 k_hough_vote(const u32 *__restrict__ queue, int *__restrict__ counters, const float *__restrict__ trig,
              int32_t *__restrict__ accum, u64 *__restrict__ peaks, int peak_cap, int h, int w, int numangle,
@@ -285,10 +288,40 @@ k_hough_vote(const u32 *__restrict__ queue, int *__restrict__ counters, const fl
             while (px < 0) { px += w; py--; }
             while (px >= w) { px -= w; py++; }
         }
+        const int cntw = min(32, nedge - base);
+        if (H16) {
+            __syncwarp();
+            ((__half2 *)s_stage[warp])[lane] = __floats2half2_rn((float)px, (float)py);
+            __syncwarp();
+            const uint4 *st4 = (const uint4 *)s_stage[warp];  // four staged pixels per entry
+            if (cntw == 32) {
+#pragma unroll
+                for (int i = 0; i < 8; i += PPW) {
+                    const uint4 v = st4[i + sub];
+                    const float2 p0 = __half22float2(*(const __half2 *)&v.x), p1 = __half22float2(*(const __half2 *)&v.y);
+                    const float2 p2 = __half22float2(*(const __half2 *)&v.z), p3 = __half22float2(*(const __half2 *)&v.w);
+                    vote(p0.x, p0.y, true);
+                    vote(p1.x, p1.y, true);
+                    vote(p2.x, p2.y, true);
+                    vote(p3.x, p3.y, true);
+                }
+            } else {
+                for (int i = 0; i < 8; i += PPW) {
+                    const uint4 v = st4[i + sub];
+                    const float2 p0 = __half22float2(*(const __half2 *)&v.x), p1 = __half22float2(*(const __half2 *)&v.y);
+                    const float2 p2 = __half22float2(*(const __half2 *)&v.z), p3 = __half22float2(*(const __half2 *)&v.w);
+                    const int k0 = 4 * (i + sub);
+                    vote(p0.x, p0.y, k0 < cntw);
+                    vote(p1.x, p1.y, k0 + 1 < cntw);
+                    vote(p2.x, p2.y, k0 + 2 < cntw);
+                    vote(p3.x, p3.y, k0 + 3 < cntw);
+                }
+            }
+            continue;
+        }
         __syncwarp();
         s_stage[warp][lane] = make_float2((float)px, (float)py);
         __syncwarp();
-        const int cntw = min(32, nedge - base);
         if (cntw == 32) {
 #pragma unroll 4
             for (int i = 0; i < 16; i += PPW) {
@@ -427,7 +460,7 @@ k_hough_vote(const u32 *__restrict__ queue, int *__restrict__ counters, const fl
     asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
-template <int A, bool HALO>
+template <int A, bool HALO, bool H16>
 static int launch_vote(le_ctx *ctx, int n, int h, int w, int numangle, int numrho, int stride, int threshold,
                        int32_t *accum, int peak_cap, float rho, float theta, float *lines, int32_t *votes,
                        int32_t *counts, int max_lines, cudaStream_t st)
@@ -435,13 +468,13 @@ static int launch_vote(le_ctx *ctx, int n, int h, int w, int numangle, int numrh
     size_t smem = (size_t)A * stride * 2;
     static size_t attr = 0;
     if (smem > attr) {
-        LE_CUDA(ctx, cudaFuncSetAttribute(k_hough_vote<A, HALO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        LE_CUDA(ctx, cudaFuncSetAttribute(k_hough_vote<A, HALO, H16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr = smem;
     }
     constexpr int OUT = HALO ? A - 2 : A;
     int stripes = (numangle + OUT - 1) / OUT;
     LE_T0(ctx, LE_K_VOTE, st);
-    k_hough_vote<A, HALO><<<dim3(stripes, n), HV_THREADS, smem, st>>>(
+    k_hough_vote<A, HALO, H16><<<dim3(stripes, n), HV_THREADS, smem, st>>>(
         (const u32 *)ctx->queue.p, (int *)ctx->counters.p, (const float *)ctx->trig.p, accum, (u64 *)ctx->peaks.p,
         peak_cap, h, w, numangle, numrho, stride, threshold, rho, theta, lines, votes, counts, max_lines,
         (u64 *)ctx->misc.p);
@@ -505,7 +538,9 @@ extern "C" int le_hough_lines(le_ctx *ctx, const uint8_t *edges, int n, int h, i
     }
     // without halo rows when the accumulator is written (the deferred boundary test reads it back)
     const bool nohalo = accum != nullptr && A >= 4;
-#define LE_VOTE(AA, HH) launch_vote<AA, HH>(ctx, n, h, w, numangle, numrho, stride, threshold, accum, peak_cap, (float)rho, \
+    static const int no_h16 = getenv("LE_VOTE_F32") ? 1 : 0;  // development knob: float2 staging everywhere
+    const bool h16 = h <= 2048 && w <= 2048 && !no_h16;
+#define LE_VOTE(AA, HH) (h16 ? launch_vote<AA, HH, true> : launch_vote<AA, HH, false>)(ctx, n, h, w, numangle, numrho, stride, threshold, accum, peak_cap, (float)rho, \
                                             (float)theta, lines, votes, counts, max_lines, st)
     if (A == 32) rc = nohalo ? LE_VOTE(32, false) : LE_VOTE(32, true);
     else if (A == 16) rc = nohalo ? LE_VOTE(16, false) : LE_VOTE(16, true);
