@@ -101,6 +101,9 @@ int le_hough_upload_trig(le_ctx *ctx, int kind, int h, int w, double rho, double
 #ifndef HV_MINB
 #define HV_MINB 3  // resident CTAs per SM the stripe height is chosen for
 #endif
+#ifndef HV_PAIR_WRITE
+#define HV_PAIR_WRITE 1  // write-out in which a lane owns both rows of its histogram word (0: one row per lane)
+#endif
 #define HV_CAND_CAP 8192   // per-frame list of peak candidates on stripe-boundary rows
 
 // Shared histogram of a stripe: u16 counters, two ANGLE ROWS per 32-bit word, bin-major:
@@ -340,6 +343,88 @@ k_hough_vote(const u32 *__restrict__ queue, int *__restrict__ counters, const fl
     __syncthreads();
 
     // ---- write the supports of the stripe's accumulator rows + peak test
+#if HV_PAIR_WRITE
+    // (2) the supports: lane = (word column kc, bin group g).  A histogram word holds the same bin of TWO rows, so
+    // a lane gathers four consecutive bins of its column once (bank-rotated: the groups of a column read the four
+    // bins in different order) and owns both rows: two 16-byte stores, each to its own global row (every row's
+    // origin was shifted so that the store is aligned).  Against one row per lane: half the gathers, and a store
+    // instruction covers A/2 rows in runs of 64 bytes instead of A rows in runs of 32.  Peaks are tested from
+    // shared memory.
+    {
+        constexpr int NC = A / 2, G = 32 / NC;
+        const int kc = lane % NC, gq = lane / NC;
+        const u32 *col = hist + kc;
+        int ar[2], nr[2], cl[2];
+        bool orow[2], there[2];
+        int32_t *outp[2];
+#pragma unroll
+        for (int r = 0; r < 2; r++) {
+            ar[r] = 2 * kc + r;
+            nr[r] = n_first - A0 + ar[r];
+            const bool ok = nr[r] >= 0 && nr[r] < numangle;
+            orow[r] = ar[r] >= A0 && ar[r] < A0 + OUT && nr[r] < n_last && ok;
+            // rows whose two neighbour rows are in this stripe (or do not exist) are tested here
+            there[r] = (ar[r] >= 1 || nr[r] == 0) && (ar[r] <= A - 2 || nr[r] == numangle - 1);
+            cl[r] = roff + s_rlo[ar[r]];
+            outp[r] = (acc_f && orow[r]) ? acc_f + (size_t)(nr[r] + 1) * rowlen + cl[r] : nullptr;
+        }
+        if (orow[0] || orow[1]) {
+            for (int b0 = 4 * (warp * G + gq); b0 < stride; b0 += 4 * G * nwarps) {
+                u32 wq[4], wd[4];
+#pragma unroll
+                for (int k = 0; k < 4; k++) wq[k] = col[(b0 + ((k + gq) & 3)) * NC];  // wq[k] = bin b0 + ((k + gq) & 3)
+#pragma unroll
+                for (int m = 0; m < 4; m++) {  // wd[m] = bin b0 + m = wq[(m - gq) & 3]
+                    const u32 t0 = (gq & 1) ? wq[(m + 3) & 3] : wq[m];
+                    const u32 t2 = (gq & 1) ? wq[(m + 1) & 3] : wq[(m + 2) & 3];
+                    wd[m] = (gq & 2) ? t2 : t0;
+                }
+#pragma unroll
+                for (int r = 0; r < 2; r++) {
+                    if (!orow[r]) continue;
+                    int v[4];
+#pragma unroll
+                    for (int m = 0; m < 4; m++) v[m] = (int)((wd[m] >> (16 * r)) & 0xffff);
+                    const int c = cl[r] + b0;
+                    if (outp[r]) {
+                        if (c >= 0 && c + 3 < rowlen)
+                            *(int4 *)(outp[r] + b0) = make_int4(v[0], v[1], v[2], v[3]);
+                        else {
+#pragma unroll
+                            for (int k = 0; k < 4; k++)
+                                if (c + k >= 0 && c + k < rowlen) outp[r][b0 + k] = v[k];
+                        }
+                    }
+                    if (max(max(v[0], v[1]), max(v[2], v[3])) <= threshold) continue;  // nothing above the threshold
+                    const int a_r = ar[r], n_r = nr[r];
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        const int cc = c + k, b = b0 + k;
+                        if (v[k] > threshold && cc >= 1 && cc <= numrho) {
+                            int left = hist_get<A>(hist, a_r, b - 1, stride), right = hist_get<A>(hist, a_r, b + 1, stride);
+                            int up = 0, down = 0;  // a neighbour row of another stripe counts as 0 here
+                            if (n_r - 1 >= 0 && a_r >= 1)
+                                up = hist_get<A>(hist, a_r - 1, cc - roff - s_rlo[a_r - 1], stride);
+                            if (n_r + 1 < numangle && a_r <= A - 2)
+                                down = hist_get<A>(hist, a_r + 1, cc - roff - s_rlo[a_r + 1], stride);
+                            if (v[k] > left && v[k] >= right && v[k] > up && v[k] >= down) {
+                                const u32 idx = (u32)((n_r + 1) * rowlen + cc);
+                                const u64 key = ((u64)(u32)v[k] << 32) | (u64)(0xffffffffu - idx);
+                                if (there[r]) {
+                                    int pos = atomicAdd(&cnt[LE_C_PEAKS], 1);
+                                    if (pos < peak_cap) pk[pos] = key;
+                                } else {
+                                    int pos = atomicAdd(&cnt[LE_C_AUX1], 1);
+                                    if (pos < HV_CAND_CAP) cand[(size_t)f * HV_CAND_CAP + pos] = key;
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    }
+#else
     // (2) the supports: lane = (row a, slot sub); a warp step covers 4 * PPW bins of every row of the
     // stripe -- each lane gathers four consecutive bins of ITS row and stores 16 bytes to ITS global row
     // (the row origin was shifted so that this store is aligned); peaks are tested from shared memory
@@ -394,6 +479,7 @@ k_hough_vote(const u32 *__restrict__ queue, int *__restrict__ counters, const fl
             }
         }
     }
+#endif
     __shared__ int s_last;
     // ---- the last CTA of the frame to get here orders the frame's peaks (its histogram is free by then)
     // The CTA's rows and peak keys must be visible before it signals: the barrier orders every thread's writes
