@@ -277,11 +277,16 @@ k_hough_vote(const u32 *__restrict__ queue, int *__restrict__ counters, const fl
         }
         if (issued) asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     }
+    int p_next = warp * 32 + lane < nedge ? (int)q[warp * 32 + lane] : 0;
     for (int base = warp * 32; base < nedge; base += nwarps * 32) {
         // each lane converts one queue entry to float (x, y) and stages it; the warp then votes the
-        // 32 pixels, two per broadcast LDS.128 (lanes = angles, so no two lanes share a row)
-        int idx = base + lane;
-        int p = idx < nedge ? (int)q[idx] : 0;
+        // 32 pixels, two per broadcast LDS.128 (lanes = angles, so no two lanes share a row).  The entry of the
+        // warp's next batch is fetched now, so its L2 round trip runs beside the votes of this one.
+        const int p = p_next;
+        {
+            const int nidx = base + nwarps * 32 + lane;
+            p_next = nidx < nedge ? (int)q[nidx] : 0;
+        }
         int py = (int)((float)p * rw);  // estimate of p / w, then exact correction
         int px = p - py * w;
         if (small) {  // p < 2^24 is exact in float and the estimate is off by one at most: two selects, no loop
