@@ -5,14 +5,15 @@
 // owns one frame and a stripe of A angles (A-2 output rows + 1 halo row each side for the peak
 // test) and keeps that support as packed u16 counters in shared memory (A x stride x 2 B, two angle
 // rows per word, see hist_get).  Voting maps LANES to ANGLES: a pixel's coordinates are warp-uniform
-// (LDS.128 broadcast of two staged pixels), a lane's increment is a constant and its address one
+// (one LDS.128 brings four half2-staged pixels, two float2 ones above 2048 x 2048), a lane's increment is a constant and its address one
 // multiply-add on the bits of the magic-number-rounded float.  The kernel is bound by the SM's LSU data
 // pipe (shared atomics + gathers + stores), so the 63 % of the int32 accumulator that lies outside
 // the supports is written by the copy engine instead: bulk stores (cp.async.bulk, UBLKCP) from a
-// zeroed shared buffer.  Inside the support each lane gathers four bins of its row and stores 16
-// aligned bytes (the origin of every shared row is shifted by up to 3 bins so that bin 4k lands on a
-// 16-byte boundary of the global row).  Peaks are tested straight from shared memory, so the
-// accumulator is never re-read.
+// zeroed shared buffer, issued before the vote loop.  Inside the support a lane gathers four consecutive
+// words of its column (= four bins of two rows) and stores 16 aligned bytes to each of the two rows (the
+// origin of every shared row is shifted by up to 3 bins so that bin 4k lands on a 16-byte boundary of the
+// global row).  Peaks are tested straight from shared memory, so the accumulator is never re-read.
+// CTAs have 512 threads and three of them share an SM: one CTA's votes run beside the write-out of the others.
 #include "le_common.cuh"
 #include <vector>
 #include <stdlib.h>
@@ -111,7 +112,8 @@ int le_hough_upload_trig(le_ctx *ctx, int kind, int h, int w, double rho, double
 // A vote instruction has lane = angle row, so its increment (1 or 0x10000) is a per-lane constant and its
 // address is ONE multiply-add on the rounded float's bits -- no parity extraction, no shifts.  The two rows
 // of a word never carry into each other (a bin holds at most a few thousand votes).  Lanes of one
-// instruction spread over banks (b % (64/A)) * (A/2) + (a >> 1): about two wavefronts per shared atomic.
+// instruction spread over banks (b % (64/A)) * (A/2) + (a >> 1): measured 3.0 wavefronts per shared atomic
+// (A = 16: 8 word columns x 4 lanes into 4 banks each; the maximum over the 8 groups is ~3).
 template <int A>
 static __device__ __forceinline__ int hist_get(const u32 *hist, int a, int b, int stride)
 {
@@ -280,7 +282,7 @@ k_hough_vote(const u32 *__restrict__ queue, int *__restrict__ counters, const fl
     int p_next = warp * 32 + lane < nedge ? (int)q[warp * 32 + lane] : 0;
     for (int base = warp * 32; base < nedge; base += nwarps * 32) {
         // each lane converts one queue entry to float (x, y) and stages it; the warp then votes the
-        // 32 pixels, two per broadcast LDS.128 (lanes = angles, so no two lanes share a row).  The entry of the
+        // 32 pixels, four (half2) or two (float2) per LDS.128 (lanes = angles, so no two lanes share a row).  The entry of the
         // warp's next batch is fetched now, so its L2 round trip runs beside the votes of this one.
         const int p = p_next;
         {
