@@ -1,20 +1,26 @@
 #!/usr/bin/env python
-"""Benchmark of the line-detection hot path (BASELINE.json metric: 1080p frames/s, Canny + HoughLines).
+"""Benchmark of the line-detection hot path (BASELINE.json: frames/s of Canny + Hough / HoughLinesP / LSD chains).
 
-    python bench.py --gpus N --steps K --warmup W            # this engine
-    python bench.py --impl reference --gpus N ...              # the reference's cv2 CPU path
+    python bench.py --gpus N --steps K --warmup W [--workload NAME]      # this engine
+    python bench.py --impl reference --gpus N ... [--workload NAME]        # the reference's cv2 CPU path
 
-Workload (BASELINE.json configs[1]): a batch of 256 synthetic 1920x1080 cube-edge BGR frames per
-GPU; one step = gray -> GaussianBlur(5,5) -> Canny(5,10) -> HoughLines(1, pi/180, 50) with the
-full int32 accumulator written (the get_camera_angles 'hough' chain, opencv_fit_color.py:74-83).
-Prints ONE JSON line (see the task contract): value = whole-job frames/s with inputs resident in
-HBM; e2e = the same through the host-buffer API (pinned host frames, H2D + D2H inside the timed
-region); roofline = the dominant kernel's algorithmic bytes / its live CUDA-event duration vs the
-measured HBM peak; cpu_baseline = the reference's cv2 chain timed on this box's cores.
+Workloads (BASELINE.json configs 2-5; one step = one pass of the chain over one batch per GPU):
+  canny_hough_1080p_b256  (default) 256 cube-edge 1080p frames: gray -> GaussianBlur(5,5) -> Canny(5,10) ->
+                          HoughLines(1, pi/180, 50), full int32 accumulator written (opencv_fit_color.py:74-83)
+  canny_houghp_4k_b128    128 cube-edge 4K frames: prob() = gray -> Canny(5,150) -> HoughLinesP(1, pi/180, 30, 50, 10)
+                          in cv2's exact pixel visiting order (opencv.py:211-219); 1024 frames over 8 GPUs
+  lsd_1080p_b512          512 voxel-world 1080p frames: lsd() = gray -> LSD(refine 0, scale .8) (opencv.py:204-209)
+  lines_1080p_cave_b128   128 cave-style 1080p frames: get_camera_angles(method='lsd') = lsd -> polar lines ->
+                          vanishing-point fit with Gaussian-sphere seeds (opencv_fit_color.py:85-93)
+Prints ONE JSON line (see the task contract): value = whole-job frames/s with inputs resident in HBM; e2e = the same
+through the host-buffer API (pinned host frames, H2D + D2H inside the timed region); roofline = the dominant
+kernel's algorithmic bytes / its live CUDA-event duration vs the measured HBM peak; cpu_baseline = the reference's
+cv2 chain timed on this box's cores; parity_sample = frames of the TIMED batch compared with cv2 after timing.
 """
 import argparse
 import json
 import os
+import statistics
 import subprocess
 import sys
 import threading
@@ -25,21 +31,165 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-H, W = 1080, 1920
-BATCH = 256
-UNIQUE = 32  # distinct synthetic frames, tiled cyclically to the batch (generation cost only)
-CANNY_LO, CANNY_HI, HOUGH_THR = 5, 10, 50
-METRIC = "1080p frames/s Canny+HoughLines (batch of 256 synthetic cube-edge frames per GPU)"
+
+# ----------------------------------------------------------------------------------------------- workloads
+class Workload:
+    """Static description + the reference's cv2 chain.  Engine-side state lives in ``EngineRun``."""
+    name = metric = kind = ""
+    h = w = batch = unique = 0
+    ref_step_frames_per_core = 2  # frames per core in one step of the --impl reference arm
+
+    def config(self):
+        """The ``config`` object of the JSON line: identical in both arms."""
+        return {"workload": self.name, "height": self.h, "width": self.w, "batch_per_gpu": self.batch,
+                "scene": self.kind, "unique_frames": self.unique, "chain": self.chain,
+                "l2": f"inputs larger than L2 ({self.batch * self.h * self.w * 3 / 1e6:.0f} MB BGR per step)"}
+
+    def chain_bytes(self):
+        """compulsory HBM bytes per frame of the whole chain."""
+        raise NotImplementedError
+
+    def cv2_chain(self, cv, frame):
+        raise NotImplementedError
+
+    def cv2_stages(self, cv, frame):
+        """[(stage name, seconds)] for one frame, the reference's calls one by one."""
+        raise NotImplementedError
+
+    needs_processes = False  # the reference chain holds the GIL (pure-Python search): pool of processes
 
 
-def algorithmic_bytes(h, w):
-    """compulsory HBM traffic per frame of the Canny+HoughLines chain."""
-    numrho = 2 * (w + h) + 1
-    front = 3 * w * h + w * h          # BGR in + edge map out        (front_nms kernel)
-    accum = 4 * 182 * (numrho + 2)     # int32 accumulator out        (hough_vote kernel)
-    return front, accum
+class CannyHough(Workload):
+    name = "canny_hough_1080p_b256"
+    metric = "1080p frames/s Canny+HoughLines (batch of 256 synthetic cube-edge frames per GPU)"
+    h, w, batch, unique, kind = 1080, 1920, 256, 32, "cubes"
+    chain = {"canny": [5, 10], "blur": "5x5", "hough": [1, "pi/180", 50], "accumulator_written": True}
+    ref_step_frames_per_core = 16
+    LO, HI, THR = 5, 10, 50
+
+    def chain_bytes(self):
+        numrho = 2 * (self.w + self.h) + 1
+        return 3 * self.w * self.h + self.w * self.h + 4 * 182 * (numrho + 2)
+
+    def kernel_bytes(self):
+        numrho = 2 * (self.w + self.h) + 1
+        return {"front_nms": 4 * self.w * self.h, "hough_vote": 4 * 182 * (numrho + 2)}
+
+    def cv2_chain(self, cv, frame):  # opencv_fit_color.py:74-83, verbatim
+        gray = cv.cvtColor(frame, cv.COLOR_BGR2GRAY)
+        blurred = cv.GaussianBlur(gray, (5, 5), 0)
+        canny = cv.Canny(blurred, self.LO, self.HI)
+        return cv.HoughLines(canny, 1, np.pi / 180, self.THR, None, 0, 0)
+
+    def cv2_stages(self, cv, frame):
+        t = [time.perf_counter()]
+        gray = cv.cvtColor(frame, cv.COLOR_BGR2GRAY); t.append(time.perf_counter())
+        blurred = cv.GaussianBlur(gray, (5, 5), 0); t.append(time.perf_counter())
+        canny = cv.Canny(blurred, self.LO, self.HI); t.append(time.perf_counter())
+        cv.HoughLines(canny, 1, np.pi / 180, self.THR, None, 0, 0); t.append(time.perf_counter())
+        return list(zip(("cvtColor", "GaussianBlur", "Canny", "HoughLines"), np.diff(t)))
 
 
+class CannyHoughP(Workload):
+    name = "canny_houghp_4k_b128"
+    metric = "4K frames/s Canny+HoughLinesP, cv2's exact visiting order (batch of 128 synthetic cube-edge frames per GPU)"
+    h, w, batch, unique, kind = 2160, 3840, 128, 16, "cubes"
+    chain = {"canny": [5, 150], "houghp": [1, "pi/180", 30, 50, 10], "order": "exact (cv::RNG replay)"}
+
+    def chain_bytes(self):  # 3WH + WH (+ 16 B per segment)
+        return 4 * self.w * self.h
+
+    def kernel_bytes(self):
+        # front: BGR in + edge map out; edge list: edge map in; PPHT proper has no compulsory HBM traffic beyond
+        # the edge map it is handed (its accumulator and mask are scratch): charged the edge map once
+        return {"front_nms": 4 * self.w * self.h, "ppht_prep": self.w * self.h, "ppht": self.w * self.h}
+
+    def cv2_chain(self, cv, frame):  # opencv.py:213-217
+        gray = cv.cvtColor(frame, cv.COLOR_BGR2GRAY)
+        edges = cv.Canny(gray, 5, 150, apertureSize=3)
+        return cv.HoughLinesP(edges, 1, np.pi / 180, threshold=30, minLineLength=50, maxLineGap=10)
+
+    def cv2_stages(self, cv, frame):
+        t = [time.perf_counter()]
+        gray = cv.cvtColor(frame, cv.COLOR_BGR2GRAY); t.append(time.perf_counter())
+        edges = cv.Canny(gray, 5, 150, apertureSize=3); t.append(time.perf_counter())
+        cv.HoughLinesP(edges, 1, np.pi / 180, threshold=30, minLineLength=50, maxLineGap=10); t.append(time.perf_counter())
+        return list(zip(("cvtColor", "Canny", "HoughLinesP"), np.diff(t)))
+
+
+def _cv_lsd(cv, gray):  # opencv.py:206-207 with lsd()'s defaults
+    det = cv.createLineSegmentDetector(0, scale=0.8, sigma_scale=0.6, quant=2.0, ang_th=22.5, log_eps=0.0,
+                                       density_th=0.7, n_bins=1024)
+    return det.detect(gray)[0]
+
+
+class Lsd(Workload):
+    name = "lsd_1080p_b512"
+    metric = "1080p frames/s LSD, refine 0 / scale .8 (batch of 512 synthetic voxel-world frames per GPU)"
+    h, w, batch, unique, kind = 1080, 1920, 512, 32, "voxel"
+    chain = {"lsd": {"refine": 0, "scale": 0.8, "sigma_scale": 0.6, "quant": 2.0, "ang_th": 22.5, "log_eps": 0.0,
+                     "density_th": 0.7, "n_bins": 1024}}
+
+    def chain_bytes(self):  # 3WH (+ 16 B per segment)
+        return 3 * self.w * self.h
+
+    def kernel_bytes(self):
+        return {"lsd_prep": self.w * self.h, "lsd_grow": 0, "misc": 4 * self.w * self.h}
+
+    def cv2_chain(self, cv, frame):
+        return _cv_lsd(cv, cv.cvtColor(frame, cv.COLOR_BGR2GRAY))
+
+    def cv2_stages(self, cv, frame):
+        t = [time.perf_counter()]
+        gray = cv.cvtColor(frame, cv.COLOR_BGR2GRAY); t.append(time.perf_counter())
+        _cv_lsd(cv, gray); t.append(time.perf_counter())
+        return list(zip(("cvtColor", "LSD.detect"), np.diff(t)))
+
+
+class LinesVp(Workload):
+    name = "lines_1080p_cave_b128"
+    metric = "1080p frames/s --pipeline lines: LSD + vanishing-point fit (batch of 128 synthetic cave-style frames per GPU)"
+    h, w, batch, unique, kind = 1080, 1920, 128, 16, "cave"
+    chain = {"lsd": Lsd.chain["lsd"], "min_segment_px": 10, "regress_lines": [1000, 500, 0.3],
+             "focal_frame": "frame size (the reference hard-codes its 600x400 fixture size)"}
+    ref_step_frames_per_core = 1
+    needs_processes = True
+    n_az, n_el = 360, 90
+
+    def chain_bytes(self):  # LSD bytes + 4 n_az n_el histogram out
+        return 3 * self.w * self.h + 4 * self.n_az * self.n_el
+
+    def kernel_bytes(self):
+        return {"lsd_prep": self.w * self.h, "lsd_grow": 0, "misc": 4 * self.w * self.h}
+
+    def cv2_chain(self, cv, frame, seed=None, fast=False):  # opencv_fit_color.py:85-93 via oracle/vp_ref.py
+        from oracle import vp_ref
+        segs = _cv_lsd(cv, cv.cvtColor(frame, cv.COLOR_BGR2GRAY))
+        pairs = [] if segs is None else [(s[0, :2], s[0, 2:]) for s in segs]
+        lines = vp_ref.edges_to_polar_lines(pairs, min_len=10)
+        if len(lines) == 0:
+            return segs, lines, ((0, 0), 100000)
+        fit = vp_ref.regress_lines(lines, 1000, 500, 0.3, seed=seed, width=self.w, height=self.h,
+                                   loss=vp_ref.sum_loss_vec if fast else vp_ref.sum_loss)
+        return segs, lines, fit
+
+    def cv2_stages(self, cv, frame):
+        from oracle import vp_ref
+        t = [time.perf_counter()]
+        gray = cv.cvtColor(frame, cv.COLOR_BGR2GRAY); t.append(time.perf_counter())
+        segs = _cv_lsd(cv, gray); t.append(time.perf_counter())
+        pairs = [] if segs is None else [(s[0, :2], s[0, 2:]) for s in segs]
+        lines = vp_ref.edges_to_polar_lines(pairs, min_len=10); t.append(time.perf_counter())
+        if len(lines):
+            vp_ref.regress_lines(lines, 1000, 500, 0.3, seed=0, width=self.w, height=self.h)
+        t.append(time.perf_counter())
+        return list(zip(("cvtColor", "LSD.detect", "polar_lines", "regress_lines (Python)"), np.diff(t)))
+
+
+WORKLOADS = {c.name: c for c in (CannyHough, CannyHoughP, Lsd, LinesVp)}
+
+
+# ----------------------------------------------------------------------------------------------- helpers
 def hbm_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -79,150 +229,307 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(self.rows)}
 
 
-def cv2_chain(cv, frame):
-    """The reference's calls, verbatim (opencv_fit_color.py:74-83)."""
-    gray = cv.cvtColor(frame, cv.COLOR_BGR2GRAY)
-    blurred = cv.GaussianBlur(gray, (5, 5), 0)
-    canny = cv.Canny(blurred, CANNY_LO, CANNY_HI)
-    return cv.HoughLines(canny, 1, np.pi / 180, HOUGH_THR, None, 0, 0)
-
-
-def time_cpu_reference(frames, min_seconds=6.0):
-    """Frame-parallel pool of os.cpu_count() workers, cv2.setNumThreads(1) each (HoughLines is
-    single-threaded inside cv2, so this is the strongest honest CPU figure).  Repeats the sample until
-    ``min_seconds`` of wall time (= min_seconds * cores of CPU work).  Returns (frames/s, cores, s, n)."""
-    import cv2 as cv
-    from concurrent.futures import ThreadPoolExecutor
-    cores = os.cpu_count() or 1
-    cv.setNumThreads(1)
-    done = 0
-    with ThreadPoolExecutor(cores) as ex:
-        list(ex.map(lambda f: cv2_chain(cv, f), frames[:cores]))  # warm
-        t0 = time.perf_counter()
-        while True:
-            list(ex.map(lambda f: cv2_chain(cv, f), frames))
-            done += len(frames)
-            dt = time.perf_counter() - t0
-            if dt >= min_seconds:
-                break
-    return done / dt, cores, dt, done
-
-
-def run_reference(args, rank, world):
-    """--impl reference: the reference's own CPU implementation (cv2 4.13 wheel of this image)."""
-    if rank != 0:
-        return
-    from graphics_project_b200_synth import make_batch
-    sample = BATCH
-    frames = list(make_batch(sample, H, W, unique=min(UNIQUE, sample)))
-    import cv2 as cv
-    from concurrent.futures import ThreadPoolExecutor
-    cores = os.cpu_count() or 1
-    cv.setNumThreads(1)
-    with ThreadPoolExecutor(cores) as ex:
-        for _ in range(args.warmup):
-            list(ex.map(lambda f: cv2_chain(cv, f), frames))
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            list(ex.map(lambda f: cv2_chain(cv, f), frames))
-        dt = time.perf_counter() - t0
-    fps = sample * args.steps / dt
-    line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": "canny_hough_1080p_b256", "height": H, "width": W, "batch_per_gpu": BATCH,
-                       "step_sample_frames": sample, "canny": [CANNY_LO, CANNY_HI], "blur": "5x5",
-                       "hough": [1, "pi/180", HOUGH_THR]},
-            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "reference",
-                             "sample": f"{sample} of the {BATCH} frames per step, cv2 {cv.__version__}, "
-                                       f"frame-parallel pool of {cores} threads, setNumThreads(1)"},
-            "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
-
-
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
-    ap.add_argument("--batch", type=int, default=BATCH, help="frames per GPU per step")
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--streams", type=int, default=int(os.environ.get("LE_BENCH_STREAMS", "1")),
-                    help="slices of the batch processed on separate CUDA streams (kernels of different slices overlap)")
-    args = ap.parse_args()
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-
-    # the synthetic generator is importable without loading the CUDA library
+def load_synth():
+    """The synthetic generator is importable without loading the CUDA library."""
     import importlib.util
     spec = importlib.util.spec_from_file_location("graphics_project_b200_synth",
                                                   os.path.join(ROOT, "graphics-project_b200", "synth.py"))
     synth = importlib.util.module_from_spec(spec)
     sys.modules["graphics_project_b200_synth"] = synth
     spec.loader.exec_module(synth)
+    return synth
 
-    if args.impl == "reference":
-        return run_reference(args, rank, world)
 
+# process-pool worker of the `lines` reference chain (pure-Python search: threads would serialise on the GIL)
+_WL = None
+
+
+def _pool_init(name):
+    global _WL
+    import cv2 as cv
+    cv.setNumThreads(1)
+    _WL = WORKLOADS[name]()
+
+
+def _pool_chain(frame):
+    import cv2 as cv
+    r = _WL.cv2_chain(cv, frame)
+    return r[2] if isinstance(r, tuple) else (0 if r is None else len(r))
+
+
+class CpuPool:
+    """Frame-parallel pool of os.cpu_count() workers with cv2.setNumThreads(1) each: HoughLines, HoughLinesP and
+    LSD are single-threaded inside cv2, so this is the strongest honest CPU figure.  Threads (cv2 releases the
+    GIL) unless the chain runs Python code, then processes."""
+
+    def __init__(self, wl):
+        import cv2 as cv
+        from concurrent.futures import ThreadPoolExecutor, ProcessPoolExecutor
+        self.cv, self.wl = cv, wl
+        self.cores = os.cpu_count() or 1
+        cv.setNumThreads(1)
+        if wl.needs_processes:
+            self.ex = ProcessPoolExecutor(self.cores, initializer=_pool_init, initargs=(wl.name,))
+            self.fn = _pool_chain
+        else:
+            self.ex = ThreadPoolExecutor(self.cores)
+            self.fn = lambda f: wl.cv2_chain(cv, f)
+        self.kind = "processes" if wl.needs_processes else "threads"
+
+    def run(self, frames):
+        return list(self.ex.map(self.fn, frames))
+
+    def close(self):
+        self.ex.shutdown()
+
+
+def time_cpu_reference(wl, frames, min_seconds=6.0):
+    """Repeats the sample until ``min_seconds`` of wall time.  Returns (frames/s, cores, seconds, frames, kind)."""
+    pool = CpuPool(wl)
+    pool.run(frames[:pool.cores])  # warm
+    done, t0 = 0, time.perf_counter()
+    while True:
+        pool.run(frames)
+        done += len(frames)
+        dt = time.perf_counter() - t0
+        if dt >= min_seconds:
+            break
+    pool.close()
+    return done / dt, pool.cores, dt, done, pool.kind
+
+
+def cpu_detail(wl, frames, budget_s=8.0):
+    """BASELINE.md section 3 / SURVEY 8(d): per-stage times (median over the sample, one frame at a time) and the
+    end-to-end chain frame by frame with cv2.setNumThreads(os.cpu_count()) -- best of 5 passes and median."""
+    import cv2 as cv
+    cores = os.cpu_count() or 1
+    cv.setNumThreads(cores)
+    stages = {}
+    t_end = time.perf_counter() + budget_s / 2
+    for f in frames:
+        for name, s in wl.cv2_stages(cv, f):
+            stages.setdefault(name, []).append(s * 1e3)
+        if time.perf_counter() > t_end:
+            break
+    passes = []
+    n = min(len(frames), max(1, len(next(iter(stages.values())))))
+    t_end = time.perf_counter() + budget_s / 2
+    for _ in range(5):
+        t0 = time.perf_counter()
+        for f in frames[:n]:
+            wl.cv2_chain(cv, f)
+        passes.append(n / (time.perf_counter() - t0))
+        if time.perf_counter() > t_end:
+            break
+    cv.setNumThreads(1)
+    return {"stages_ms_median": {k: round(statistics.median(v), 3) for k, v in stages.items()},
+            "stage_sample_frames": len(next(iter(stages.values()))),
+            "setNumThreads_all": {"threads": cores, "frames_per_pass": n, "passes": len(passes),
+                                  "fps_best": max(passes), "fps_median": statistics.median(passes)}}
+
+
+def make_frames(synth, wl, n, rank):
+    uniq = synth.make_batch(min(wl.unique, n), wl.h, wl.w, wl.kind, first_seed=rank * 1000)
+    return [uniq[i % len(uniq)] for i in range(n)], uniq
+
+
+def run_reference(args, wl, rank):
+    """--impl reference: the reference's own CPU implementation (the cv2 wheel of this image; the `lines` workload
+    adds oracle/vp_ref.py, the restatement of the reference's pure-Python search)."""
+    if rank != 0:
+        return
+    synth = load_synth()
+    pool = CpuPool(wl)
+    sample = max(1, wl.ref_step_frames_per_core * pool.cores)
+    frames, _ = make_frames(synth, wl, sample, 0)
+    import cv2 as cv
+    for _ in range(args.warmup):
+        pool.run(frames)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        pool.run(frames)
+    dt = time.perf_counter() - t0
+    pool.close()
+    fps = sample * args.steps / dt
+    line = {"impl": "reference", "metric": wl.metric, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": wl.config(),
+            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": pool.cores, "kind": "reference",
+                             "sample": f"{sample} frames of the workload per step, cv2 {cv.__version__}, "
+                                       f"frame-parallel pool of {pool.cores} {pool.kind}, setNumThreads(1)"},
+            "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------- engine arm
+def seg_match(a, b, tol):
+    """LSD criterion: same count, endpoints within ``tol`` px in order (either orientation)."""
+    if len(a) != len(b):
+        return False
+    if len(a) == 0:
+        return True
+    d0 = np.abs(a - b).max(1)
+    d1 = np.abs(a - b[:, [2, 3, 0, 1]]).max(1)
+    return bool((np.minimum(d0, d1) <= tol).all())
+
+
+class EngineRun:
+    """Device-resident state of one workload on one GPU: buffers, the step, results, the host pipeline, parity."""
+
+    def __init__(self, wl, gp, torch, dev, frames, B):
+        self.wl, self.gp, self.torch, self.dev, self.frames, self.B = wl, gp, torch, dev, frames, B
+        self.eng = gp.Engine(dev.index, wl.h, wl.w, B)
+        self.i = 0
+        name = wl.name
+        mk = lambda *s, dt: torch.empty(s, dtype=dt, device=dev)  # noqa: E731
+        if name == CannyHough.name:
+            self.max_k = 1024
+            na, nr = self.eng.hough_dims(wl.h, wl.w)
+            self.edges = mk(B, wl.h, wl.w, dt=torch.uint8)
+            self.accum = mk(B, na + 2, nr + 2, dt=torch.int32)
+            # two result sets: with N > 1 the gather of step i runs beside the kernels of step i + 1
+            self.payload2 = [mk(B, self.max_k, 2, dt=torch.float32) for _ in range(2)]
+            self.counts2 = [mk(B, dt=torch.int32) for _ in range(2)]
+        elif name == CannyHoughP.name:
+            self.max_k = 1024
+            self.edges = mk(B, wl.h, wl.w, dt=torch.uint8)
+        elif name == Lsd.name:
+            self.max_k = 2048
+            self.gray = mk(B, wl.h, wl.w, dt=torch.uint8)
+        else:
+            self.max_k = 2048
+        self.payload = self.counts = self.extra = None
+
+    # one pass of the chain over the resident batch, on the current stream
+    def step(self):
+        wl, eng, name = self.wl, self.eng, self.wl.name
+        if name == CannyHough.name:
+            self.payload, self.counts = self.payload2[self.i & 1], self.counts2[self.i & 1]
+            eng.front_canny(self.frames, wl.LO, wl.HI, blur=True, out=self.edges)
+            eng.hough_lines(None, 1.0, np.pi / 180, wl.THR, out=(self.payload, None, self.counts, self.accum))
+        elif name == CannyHoughP.name:
+            eng.front_canny(self.frames, 5, 150, out=self.edges)
+            self.payload, self.counts = eng.hough_lines_p(self.edges, 1, np.pi / 180, 30, 50, 10, max_segs=self.max_k)
+        elif name == Lsd.name:
+            gray = eng.bgr2gray(self.frames)
+            self.payload, _, _, self.counts = eng.lsd(gray, max_segs=self.max_k)
+        else:
+            fit, hist, polar, pcounts, segs, counts = self.gp.vp.get_camera_angles_batch(
+                self.frames, 1000, 500, max_segs=self.max_k, engine=eng)
+            self.payload, self.counts, self.extra = fit, pcounts, (hist, polar, segs, counts)
+        self.i += 1
+
+    def gather_args(self):
+        return self.counts, self.payload
+
+    def pipeline(self, chunk=None):
+        wl, P, d = self.wl, self.gp.pipeline, self.dev.index
+        torch = self.torch
+        pin = lambda *s, dt: torch.empty(s, dtype=dt, pin_memory=True)  # noqa: E731
+        B, k = self.B, self.max_k
+        if wl.name == CannyHough.name:
+            return (P.CannyHoughHost(wl.h, wl.w, d, chunk=chunk or 32, max_lines=k, lo=wl.LO, hi=wl.HI, blur=True,
+                                     threshold=wl.THR),
+                    [pin(B, k, 2, dt=torch.float32), pin(B, dt=torch.int32)], "CannyHoughHost")
+        if wl.name == CannyHoughP.name:
+            return (P.ProbHost(wl.h, wl.w, d, chunk=chunk or 16, max_segs=k),
+                    [pin(B, k, 4, dt=torch.int32), pin(B, dt=torch.int32)], "ProbHost")
+        if wl.name == Lsd.name:
+            return (P.LsdHost(wl.h, wl.w, d, chunk=chunk or 64, max_segs=k),
+                    [pin(B, k, 4, dt=torch.float32), pin(B, dt=torch.int32)], "LsdHost")
+        return (P.LinesVpHost(wl.h, wl.w, d, chunk=chunk or 32, max_segs=k),
+                [pin(B, 3, dt=torch.float64), pin(B, dt=torch.int32)], "LinesVpHost")
+
+    def parity_sample(self, host_frames, idxs):
+        """Frames of the TIMED batch (results of the last timed step still in the buffers) against cv2 on the same
+        host frames: bit-exact for Canny / HoughLines / HoughLinesP, 0.5 px for LSD; the VP fit is graded by the
+        reference's own loss against three seeded runs of the reference's search."""
+        import cv2 as cv
+        wl, name = self.wl, self.wl.name
+        cv.setNumThreads(os.cpu_count() or 1)
+        ok, detail = True, []
+        counts = self.counts.cpu().numpy()
+        for i in idxs:
+            f = host_frames[i].numpy()
+            if name == CannyHough.name:
+                gray = cv.cvtColor(f, cv.COLOR_BGR2GRAY)
+                canny = cv.Canny(cv.GaussianBlur(gray, (5, 5), 0), wl.LO, wl.HI)
+                ref = cv.HoughLines(canny, 1, np.pi / 180, wl.THR, None, 0, 0)
+                n = 0 if ref is None else len(ref)
+                e = np.array_equal(self.edges[i].cpu().numpy(), canny) and int(counts[i]) == n and (
+                    n == 0 or np.array_equal(self.payload[i, :min(n, self.max_k)].cpu().numpy(), ref[:self.max_k, 0]))
+            elif name == CannyHoughP.name:
+                edges = cv.Canny(cv.cvtColor(f, cv.COLOR_BGR2GRAY), 5, 150, apertureSize=3)
+                ref = cv.HoughLinesP(edges, 1, np.pi / 180, threshold=30, minLineLength=50, maxLineGap=10)
+                n = 0 if ref is None else len(ref)
+                e = np.array_equal(self.edges[i].cpu().numpy(), edges) and int(counts[i]) == n and (
+                    n == 0 or np.array_equal(self.payload[i, :min(n, self.max_k)].cpu().numpy(), ref[:self.max_k, 0]))
+            elif name == Lsd.name:
+                ref = _cv_lsd(cv, cv.cvtColor(f, cv.COLOR_BGR2GRAY))
+                n = 0 if ref is None else len(ref)
+                e = int(counts[i]) == n and (n == 0 or seg_match(self.payload[i, :n].cpu().numpy(), ref[:, 0], 0.5))
+            else:
+                from oracle import vp_ref
+                hist, polar, segs, scounts = self.extra
+                ref = _cv_lsd(cv, cv.cvtColor(f, cv.COLOR_BGR2GRAY))
+                n = 0 if ref is None else len(ref)
+                e = int(scounts[i]) == n and (n == 0 or seg_match(segs[i, :n].cpu().numpy(), ref[:, 0], 0.5))
+                lines = polar[i, :int(counts[i])].cpu().numpy()
+                if e and len(lines):
+                    phi, theta, loss = self.payload[i].cpu().numpy()
+                    rescored = vp_ref.sum_loss_vec(phi, theta, lines, wl.w, wl.h)
+                    runs = sorted(vp_ref.regress_lines(lines, 1000, 500, 0.3, seed=s, width=wl.w, height=wl.h,
+                                                       loss=vp_ref.sum_loss_vec)[1] for s in range(3))
+                    e = abs(rescored - loss) <= 1e-9 * max(1.0, abs(loss)) and loss <= runs[1]
+                    detail.append({"frame": int(i), "lines": len(lines), "loss": float(loss),
+                                   "reference_search_losses": [float(r) for r in runs]})
+            ok = ok and bool(e)
+        cv.setNumThreads(1)
+        crit = {CannyHough.name: "edge map, line count, (rho, theta) and order bit-exact vs cv2",
+                CannyHoughP.name: "edge map, segment count, endpoints and order bit-exact vs cv2",
+                Lsd.name: "segment count equal, endpoints within 0.5 px in cv2's order",
+                LinesVp.name: "LSD as lsd_1080p_b512; fit loss re-scored by the reference's sum_loss and <= the "
+                              "median of 3 seeded runs of the reference's search"}[name]
+        out = {"frames": len(idxs), "frame_indices": [int(i) for i in idxs], "equal": ok, "criterion": crit,
+               "cv2": cv.__version__}
+        if detail:
+            out["fits"] = detail
+        return out
+
+
+def run_engine(args, wl, rank, world, local_rank):
     import torch
     import torch.distributed as dist
     import graphics_project_b200 as gp
 
     assert torch.cuda.is_available(), "bench.py needs a GPU (the engine has no CPU fallback)"
+    synth = load_synth()
     torch.cuda.set_device(local_rank)
+    numa = gp.pipeline.bind_to_gpu_numa_node(local_rank) if not args.no_numa else {"bound": False, "skipped": True}
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
-    B = args.batch
-    max_lines = 1024
+    B = args.batch or wl.batch
 
     # ---- synthetic input: frames are generated on the host once and uploaded before timing
-    uniq = synth.make_batch(min(UNIQUE, B), H, W, first_seed=rank * 1000)
-    host_frames = torch.empty((B, H, W, 3), dtype=torch.uint8, pin_memory=True)
+    _, uniq = make_frames(synth, wl, min(wl.unique, B), rank)
+    host_frames = torch.empty((B, wl.h, wl.w, 3), dtype=torch.uint8, pin_memory=True)
     for i in range(B):
         host_frames[i] = torch.from_numpy(uniq[i % len(uniq)])
     frames = host_frames.to(dev)
-
-    S = max(1, min(args.streams, B))
-    engs = [gp.Engine(local_rank, H, W, (B + S - 1) // S) for _ in range(S)]
-    eng = engs[0]
-    side = [torch.cuda.Stream(dev) for _ in range(S)]
-    bounds = [(i * B // S, (i + 1) * B // S) for i in range(S)]
-    na, nr = eng.hough_dims(H, W)
-    edges = torch.empty((B, H, W), dtype=torch.uint8, device=dev)
-    # two result sets: with N > 1 the gather of step i runs beside the kernels of step i + 1
-    lines2 = [torch.empty((B, max_lines, 2), dtype=torch.float32, device=dev) for _ in range(2)]
-    counts2 = [torch.empty((B,), dtype=torch.int32, device=dev) for _ in range(2)]
-    lines, counts = lines2[0], counts2[0]
-    state = {"i": 0, "pending": None, "gathered": None}
-    accum = torch.empty((B, na + 2, nr + 2), dtype=torch.int32, device=dev)
+    run = EngineRun(wl, gp, torch, dev, frames, B)
+    eng = run.eng
+    state = {"pending": None, "gathered": None}
 
     def step():
-        lines, counts = lines2[state["i"] & 1], counts2[state["i"] & 1]
-        if S == 1:
-            eng.front_canny(frames, CANNY_LO, CANNY_HI, blur=True, out=edges)
-            eng.hough_lines(None, 1.0, np.pi / 180, HOUGH_THR, out=(lines, None, counts, accum))
-        else:
-            main = torch.cuda.current_stream(dev)
-            fork = torch.cuda.Event()
-            fork.record(main)
-            for e, st, (a, b) in zip(engs, side, bounds):
-                st.wait_event(fork)
-                with torch.cuda.stream(st):
-                    e.front_canny(frames[a:b], CANNY_LO, CANNY_HI, blur=True, out=edges[a:b])
-                    e.hough_lines(None, 1.0, np.pi / 180, HOUGH_THR, out=(lines[a:b], None, counts[a:b], accum[a:b]))
-                join = torch.cuda.Event()
-                join.record(st)
-                main.wait_event(join)
+        run.step()
         if world > 1:  # gather the per-frame results of the whole job (SURVEY 8e), one step behind
             if state["pending"] is not None:
                 state["gathered"] = state["pending"].wait()
-            state["pending"] = gp.dist.gather_results(counts, lines, B * world, async_op=True, slot=state["i"] & 1)
-        state["i"] += 1
+            c, p = run.gather_args()
+            state["pending"] = gp.dist.gather_results(c, p, B * world, async_op=True, slot=run.i & 1)
 
     def drain():
         if state["pending"] is not None:
@@ -239,22 +546,15 @@ def main():
         step()
     drain()
     barrier()
-    for e in engs:
-        e.check()
+    eng.check()
     sampler = ClockSampler(local_rank)
     sampler.start()
     t_load = time.perf_counter()
     while time.perf_counter() - t_load < 1.0:  # keep the GPU under load while the clock sampler collects
-        for _ in range(20):
-            step()
+        step()
         drain()
         torch.cuda.synchronize()
-    for e in engs:
-        # per-kernel events cost ~22 us per step (8 records): with one stream they are recorded in the separate
-        # roofline pass below instead (same workload, same stream); LE_BENCH_EVENTS=1 puts them back here
-        e.timing(S > 1 or os.environ.get("LE_BENCH_EVENTS", "0") == "1")
-        e.timing_read()
-    launches0 = sum(e.launches for e in engs)
+    launches0 = eng.launches
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record()
@@ -264,16 +564,9 @@ def main():
     ev1.record()
     barrier()
     ms = ev0.elapsed_time(ev1)
-    launches = sum(e.launches for e in engs) - launches0
-    ktimes = {}
-    for e in engs:
-        for k, (tms, c) in e.timing_read().items():
-            a = ktimes.get(k, (0.0, 0))
-            ktimes[k] = (a[0] + tms, a[1] + c)
-        e.timing(False)
+    launches = eng.launches - launches0
     clocks = sampler.finish()
-    for e in engs:
-        e.check()
+    eng.check()
     if world > 1:
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -282,91 +575,134 @@ def main():
         dist.all_reduce(lt)
         launches = int(lt.item())
     fps = B * world * args.steps / (ms * 1e-3)
+    want_counts = run.counts.cpu()
+    results_mean = float(want_counts.float().mean().item())
 
-    # ---- roofline of the dominant kernel.  With --streams > 1 the slices' kernels overlap on the GPU, so a
-    # kernel's event-to-event duration in the timed region includes time it shares the SMs with the other
-    # slice.  The per-launch duration used for the roofline is therefore taken live from K more steps of the
-    # same workload issued on ONE stream (whole batch per launch, kernels back to back, nothing overlapping).
-    front_b, accum_b = algorithmic_bytes(H, W)
+    # ---- parity: frames of the timed batch against cv2 (rank 0; before anything overwrites the result buffers)
+    parity = None
+    if rank == 0 and not args.no_parity:
+        idxs = sorted({0, 1, B // 2, B - 1} if B >= 4 else set(range(B)))
+        parity = run.parity_sample(host_frames, idxs)
+
+    # ---- roofline of the dominant kernel: per-launch durations from CUDA events the library records around every
+    # launch (on its launch stream), in a separate pass of K more steps of the same workload on the same stream
+    # (eight event records per step cost ~22 us, which is 2.5 % of the default workload's step)
     peak, peak_src = hbm_peak()
-    kernel_ms_overlapped = {k: v[0] / v[1] for k, v in ktimes.items()}
     eng.timing(True)
     eng.timing_read()
-    for _ in range(args.steps):
-        eng.front_canny(frames, CANNY_LO, CANNY_HI, blur=True, out=edges)
-        eng.hough_lines(None, 1.0, np.pi / 180, HOUGH_THR, out=(lines, None, counts, accum))
+    for _ in range(max(1, min(args.steps, 10))):
+        run.step()
     torch.cuda.synchronize()
-    kt1 = eng.timing_read()
+    kt = eng.timing_read()
     eng.timing(False)
-    alg = {"front_nms": front_b * B, "hough_vote": accum_b * B}  # algorithmic bytes per launch (whole batch)
-    kernel_ms = {k: v[0] / v[1] for k, v in kt1.items()}
-    dominant = max((k for k in kernel_ms if k in alg), key=lambda k: kt1[k][0])
-    achieved = alg[dominant] / (kernel_ms[dominant] * 1e-3) / 1e9
+    kernel_ms = {k: v[0] / v[1] for k, v in kt.items()}
+    kbytes = wl.kernel_bytes()
+    dominant = max(kt, key=lambda k: kt[k][0])
+    alg = kbytes.get(dominant, 0) * B
+    achieved = alg / (kernel_ms[dominant] * 1e-3) / 1e9
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
-        traffic = json.load(open(tp)).get(dominant)
+        traffic = json.load(open(tp)).get(wl.name, {}).get(dominant)
+    chain_frac = wl.chain_bytes() * B / (ms / args.steps * 1e-3) / 1e9 / peak
     roofline = {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": alg[dominant],
+                "algorithmic_bytes_per_launch": alg,
                 "kernel_ms_per_launch": kernel_ms,
-                "kernel_ms_per_launch_in_timed_region_overlapped_half_batches": kernel_ms_overlapped,
-                "step_frac_of_hbm_roofline": (front_b + accum_b) * B / (ms / args.steps * 1e-3) / 1e9 / peak}
+                "kernel_share_of_step": {k: v[0] / sum(x[0] for x in kt.values()) for k, v in kt.items()},
+                "chain_algorithmic_bytes_per_frame": wl.chain_bytes(),
+                "step_frac_of_hbm_roofline": chain_frac}
 
     # ---- e2e: host-buffer API, H2D + D2H inside the timed region
     e2e = None
     if not args.no_e2e:
-        del accum, edges
+        del run
         torch.cuda.empty_cache()
-        pipe = gp.pipeline.CannyHoughHost(H, W, local_rank, chunk=32, max_lines=max_lines, lo=CANNY_LO, hi=CANNY_HI,
-                                          blur=True, threshold=HOUGH_THR)
-        out_lines = torch.empty((B, max_lines, 2), dtype=torch.float32, pin_memory=True)
-        out_counts = torch.empty((B,), dtype=torch.int32, pin_memory=True)
+        run2 = EngineRun(wl, gp, torch, dev, frames[:0], 1)
+        pipe, outs, api = run2.pipeline(args.chunk)
         for _ in range(2):
-            pipe.run(host_frames, out_lines, out_counts)
+            pipe.run(host_frames, *outs)
         barrier()
         l0 = pipe.launches
-        t0 = time.perf_counter()
         e2e_steps = max(2, min(args.steps, 5))
+        t0 = time.perf_counter()
         for _ in range(e2e_steps):
-            pipe.run(host_frames, out_lines, out_counts)
+            pipe.run(host_frames, *outs)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
+        # copy-only ceiling: the same pinned batch through the same chunks and streams, no kernels
+        ceil_steps = 2
+        t0 = time.perf_counter()
+        for _ in range(ceil_steps):
+            for ci, c0 in enumerate(range(0, B, pipe.chunk)):
+                c1 = min(B, c0 + pipe.chunk)
+                with torch.cuda.stream(pipe.streams[ci & 1]):
+                    pipe.bufs[ci & 1]["src"][:c1 - c0].copy_(host_frames[c0:c1], non_blocking=True)
+            torch.cuda.synchronize()
+        dt_copy = (time.perf_counter() - t0) / ceil_steps
         if world > 1:
-            t = torch.tensor([dt], dtype=torch.float64, device=dev)
+            t = torch.tensor([dt, dt_copy], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
-        assert torch.equal(out_counts, counts.cpu()), "e2e results differ from the resident-input run"
+            dt, dt_copy = float(t[0].item()), float(t[1].item())
+        pipe.check()
+        assert torch.equal(outs[1], want_counts), "e2e results differ from the resident-input run"
         e2e = {"value": B * world * e2e_steps / dt, "unit": "frames/s", "h2d_bytes_per_step": pipe.h2d_bytes,
-               "d2h_bytes_per_step": pipe.d2h_bytes, "steps": e2e_steps,
-               "gpu_launches": pipe.launches - l0,
-               "api": "graphics_project_b200.pipeline.CannyHoughHost.run (pinned host frames -> host lines)"}
+               "d2h_bytes_per_step": pipe.d2h_bytes, "steps": e2e_steps, "gpu_launches": pipe.launches - l0,
+               "copy_ceiling_fps": B * world / dt_copy,
+               "copy_ceiling_gbs_per_gpu": pipe.h2d_bytes / dt_copy / 1e9,
+               "api": f"graphics_project_b200.pipeline.{api}.run (pinned host frames -> host results)",
+               "numa": numa}
 
     # ---- CPU baseline: the reference's cv2 chain on a bounded sample, rank 0 at N == 1 only
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        sample = 128
-        fps_cpu, cores, dt, done = time_cpu_reference([uniq[i % len(uniq)] for i in range(sample)])
         import cv2 as cv
+        sample = max(1, min(128, wl.ref_step_frames_per_core * (os.cpu_count() or 1) * 2))
+        fl = [uniq[i % len(uniq)] for i in range(sample)]
+        fps_cpu, cores, dt, done, kind = time_cpu_reference(wl, fl)
         cpu = {"value": fps_cpu, "unit": "frames/s", "cores": cores, "kind": "reference",
                "sample": f"{done} frames of the same workload ({sample}-frame sample repeated) in {dt:.1f} s wall = "
                          f"{dt * cores:.0f} core-seconds, cv2 {cv.__version__}, frame-parallel pool of {cores} "
-                         f"threads, setNumThreads(1)"}
+                         f"{kind}, setNumThreads(1)" + (", + oracle/vp_ref.py (the reference's Python search)"
+                                                        if wl.needs_processes else "")}
+        cpu.update(cpu_detail(wl, fl[:max(2, min(len(fl), 8))]))
 
     if rank == 0:
-        line = {"metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+        cfg = wl.config()
+        cfg["batch_per_gpu"] = B
+        line = {"metric": wl.metric, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-                "config": {"workload": "canny_hough_1080p_b256", "height": H, "width": W, "batch_per_gpu": B,
-                           "unique_frames": len(uniq), "canny": [CANNY_LO, CANNY_HI], "blur": "5x5",
-                           "hough": [1, "pi/180", HOUGH_THR], "accumulator_written": True, "streams": S,
-                           "l2": f"inputs larger than L2 ({frames.numel() / 1e6:.0f} MB BGR per step)",
-                           "lines_per_frame_mean": float(counts.float().mean().item())},
-                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks}
+                "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": cfg,
+                "results_per_frame_mean": results_mean,
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "parity_sample": parity,
+                "gpu_launches": launches, "clocks": clocks}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
+    ap.add_argument("--workload", default=CannyHough.name, choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="frames per GPU per step (default: the workload's)")
+    ap.add_argument("--chunk", type=int, default=0, help="frames per chunk of the host pipeline (e2e)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-numa", action="store_true", help="do not bind the process to the GPU's NUMA node")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    wl = WORKLOADS[args.workload]()
+    if args.impl == "reference":
+        return run_reference(args, wl, rank)
+    return run_engine(args, wl, rank, world, local_rank)
 
 
 if __name__ == "__main__":

@@ -69,6 +69,34 @@ void le_time_mark(le_ctx *ctx, int id, int end, cudaStream_t st);
 #define LE_T1(ctx, id, st) do { if ((ctx)->timing_on) le_time_mark(ctx, id, 1, st); } while (0)
 
 int le_fail(le_ctx *ctx, int code, const char *fmt, ...);
+
+// cudaFuncSetAttribute is a per-DEVICE setting: every call site remembers what it has set per device (a process
+// may hold contexts on several GPUs).  `v` is the size (or 1) already set on that device.
+#define LE_MAX_DEVICES 64
+struct le_dev_once {
+    size_t v[LE_MAX_DEVICES];
+    bool needs(int dev, size_t want) const { return dev < 0 || dev >= LE_MAX_DEVICES || v[dev] < want; }
+    void done(int dev, size_t want) { if (dev >= 0 && dev < LE_MAX_DEVICES) v[dev] = want; }
+};
+
+// Development knobs (A/B measurements, the comparison runs of the tests) are environment variables read ONCE per
+// process and call site, never on the per-call path.  `present`: the variable exists (value ignored).
+#include <stdlib.h>
+#define LE_KNOB_INT(name, dflt) ([] { static const int v = [] { const char *e = getenv(name); return e ? atoi(e) : (dflt); }(); return v; }())
+#define LE_KNOB_SET(name) ([] { static const bool v = getenv(name) != nullptr; return v; }())
+
+// Every ABI entry runs on its context's device and leaves the caller's current device as it found it.
+struct le_dev_guard {
+    int prev;
+    explicit le_dev_guard(int dev) : prev(-1)
+    {
+        if (dev < 0) return;  // null context: the entry point reports it
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev) cudaSetDevice(dev); else prev = -1;
+    }
+    ~le_dev_guard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+#define LE_ON_DEVICE(ctx) le_dev_guard le_dev_guard__((ctx) ? (ctx)->device : -1)
 int le_ensure(le_ctx *ctx, le_buf *b, size_t bytes);
 
 #define LE_CUDA(ctx, call)                                                                         \

@@ -48,6 +48,7 @@ extern "C" int le_create(le_ctx **out, int device, int max_h, int max_w, int max
     if (e != cudaSuccess || ndev <= 0)
         return le_fail(nullptr, LE_ERR_CUDA, "le_create: no CUDA device available (%s)", cudaGetErrorString(e));
     if (device < 0 || device >= ndev) return le_fail(nullptr, LE_ERR_INVALID, "le_create: bad device %d", device);
+    le_dev_guard on_device(device);  // the caller's current device is restored on return
     e = cudaSetDevice(device);
     if (e != cudaSuccess) return le_fail(nullptr, LE_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
     le_ctx *ctx = (le_ctx *)calloc(1, sizeof(le_ctx));
@@ -75,7 +76,7 @@ extern "C" int le_create(le_ctx **out, int device, int max_h, int max_w, int max
 extern "C" int le_destroy(le_ctx *ctx)
 {
     if (!ctx) return LE_OK;
-    cudaSetDevice(ctx->device);
+    LE_ON_DEVICE(ctx);
     cudaDeviceSynchronize();
     le_buf *bufs[] = {&ctx->counters, &ctx->queue, &ctx->lut, &ctx->peaks, &ctx->trig, &ctx->tmp0, &ctx->tmp1,
                       &ctx->ppht_accum, &ctx->ppht_mask, &ctx->ppht_nz, &ctx->lsd0, &ctx->lsd1, &ctx->lsd2,
@@ -126,6 +127,7 @@ extern "C" int le_timing_enable(le_ctx *ctx, int on)
 
 extern "C" int le_timing_read(le_ctx *ctx, int id, double *total_ms, int *launches)
 {
+    LE_ON_DEVICE(ctx);
     if (!ctx || id < 0 || id >= LE_K_COUNT || !total_ms || !launches) return LE_ERR_INVALID;
     double tot = 0;
     for (int i = 0; i + 1 < ctx->tn[id]; i += 2) {
@@ -150,6 +152,7 @@ __global__ void k_collect_overflow(const int *counters, int n, int *out)
 
 extern "C" int le_check(le_ctx *ctx, void *stream)
 {
+    LE_ON_DEVICE(ctx);
     if (!ctx) return LE_ERR_INVALID;
     cudaStream_t st = (cudaStream_t)stream;
     LE_CUDA(ctx, cudaStreamSynchronize(st));

@@ -153,7 +153,6 @@ static int f32_check(le_ctx *ctx, const void *a, const void *b, int n, int h, in
     LE_REQUIRE(ctx, n > 0 && h > 0 && w > 0, "n, h, w must be positive");
     LE_REQUIRE(ctx, (size_t)h * w < ((size_t)1 << 30), "frame too large");
     LE_REQUIRE(ctx, (((size_t)a | (size_t)b) & 3) == 0, "image pointers must be 4-byte aligned");
-    cudaSetDevice(ctx->device);
     return LE_OK;
 }
 
@@ -169,6 +168,7 @@ static int f32_counters(le_ctx *ctx, int n, cudaStream_t st)
 extern "C" int le_f32_bgr2gray(le_ctx *ctx, const float *src, long long stride_n, long long stride_y,
                                long long stride_x, long long stride_c, float *gray, int n, int h, int w, void *stream)
 {
+    LE_ON_DEVICE(ctx);
     int rc = f32_check(ctx, src, gray, n, h, w);
     if (rc) return rc;
     dim3 block(32, 8), grid((w + 31) / 32, (h + 7) / 8, n);
@@ -179,6 +179,7 @@ extern "C" int le_f32_bgr2gray(le_ctx *ctx, const float *src, long long stride_n
 
 extern "C" int le_f32_gauss5(le_ctx *ctx, const float *src, float *dst, int n, int h, int w, void *stream)
 {
+    LE_ON_DEVICE(ctx);
     int rc = f32_check(ctx, src, dst, n, h, w);
     if (rc) return rc;
     LE_REQUIRE(ctx, src != dst, "le_f32_gauss5 is not in-place");
@@ -201,6 +202,7 @@ static int f32_normalize_launch(le_ctx *ctx, const float *src, float *dst_f32, u
 extern "C" int le_f32_minmax_normalize(le_ctx *ctx, const float *src, float *dst_f32, uint8_t *dst_u8, int n, int h,
                                        int w, void *stream)
 {
+    LE_ON_DEVICE(ctx);
     int rc = f32_check(ctx, src, src, n, h, w);
     if (rc) return rc;
     LE_REQUIRE(ctx, dst_f32 || dst_u8, "le_f32_minmax_normalize: no output");
@@ -219,6 +221,7 @@ extern "C" int le_f32_front_canny(le_ctx *ctx, const float *src, long long strid
                                   long long stride_x, long long stride_c, uint8_t *edges, int n, int h, int w,
                                   double lo, double hi, void *stream)
 {
+    LE_ON_DEVICE(ctx);
     int rc = f32_check(ctx, src, edges, n, h, w);
     if (rc) return rc;
     LE_REQUIRE(ctx, lo == lo && hi == hi, "NaN threshold");

@@ -236,12 +236,12 @@ extern "C" int le_face_quads(le_ctx *ctx, const double *segs1, const int32_t *co
                              const int32_t *counts2, int max2, int n, double threshold, int32_t *quads, double *faces,
                              uint8_t *keep, int32_t *counts, int max_out, void *stream)
 {
+    LE_ON_DEVICE(ctx);
     if (!ctx) return LE_ERR_INVALID;
     LE_REQUIRE(ctx, segs1 && segs2 && quads && faces && keep && counts, "null pointer");
     LE_REQUIRE(ctx, n > 0 && max1 > 0 && max2 > 0 && max_out > 0, "n, max1, max2, max_out must be positive");
     if (max1 > FC_MAX || max2 > FC_MAX)
         return le_fail(ctx, LE_ERR_UNSUPPORTED, "at most %d segments per list (got %d, %d)", FC_MAX, max1, max2);
-    cudaSetDevice(ctx->device);
     cudaStream_t st = (cudaStream_t)stream;
     const size_t nw = (max2 + 31) / 32;
     const size_t b_bits = (sizeof(u32) * (size_t)n * max1 * nw + 255) & ~(size_t)255;

@@ -354,12 +354,12 @@ static int check_img(le_ctx *ctx, const void *a, const void *b, int n, int h, in
     LE_REQUIRE(ctx, n > 0 && h > 0 && w > 0, "n, h, w must be positive");
     LE_REQUIRE(ctx, (size_t)h * w < ((size_t)1 << 30), "frame too large");
     LE_REQUIRE(ctx, (((size_t)a | (size_t)b) & 3) == 0, "image pointers must be 4-byte aligned");
-    cudaSetDevice(ctx->device);
     return LE_OK;
 }
 
 extern "C" int le_bgr2gray_u8(le_ctx *ctx, const uint8_t *bgr, uint8_t *gray, int n, int h, int w, void *stream)
 {
+    LE_ON_DEVICE(ctx);
     int rc = check_img(ctx, bgr, gray, n, h, w);
     if (rc) return rc;
     size_t npx = (size_t)n * h * w;
@@ -371,6 +371,7 @@ extern "C" int le_bgr2gray_u8(le_ctx *ctx, const uint8_t *bgr, uint8_t *gray, in
 
 extern "C" int le_gauss5_u8(le_ctx *ctx, const uint8_t *src, uint8_t *dst, int n, int h, int w, void *stream)
 {
+    LE_ON_DEVICE(ctx);
     int rc = check_img(ctx, src, dst, n, h, w);
     if (rc) return rc;
     LE_REQUIRE(ctx, src != dst, "le_gauss5_u8 is not in-place");
@@ -401,6 +402,7 @@ static int minmax_lut(le_ctx *ctx, const u8 *src, int n, int h, int w, cudaStrea
 extern "C" int le_minmax_normalize_u8(le_ctx *ctx, const uint8_t *src, uint8_t *dst, int n, int h, int w,
                                       void *stream)
 {
+    LE_ON_DEVICE(ctx);
     int rc = check_img(ctx, src, dst, n, h, w);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
@@ -451,10 +453,10 @@ int le_front_launch(le_ctx *ctx, const u8 *src, int ch, int do_blur, int do_norm
     rc = le_front_rows_launch(ctx, in, in_ch, blur, do_norm, edges, n, h, w, lo, hi, st);
     if (rc) return rc;
     LE_T0(ctx, LE_K_HYST, st);
-    static bool hyst_attr = false;
-    if (!hyst_attr) {
+    static le_dev_once hyst_attr;
+    if (hyst_attr.needs(ctx->device, 65536)) {
         LE_CUDA(ctx, cudaFuncSetAttribute(k_hysteresis, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
-        hyst_attr = true;
+        hyst_attr.done(ctx->device, 65536);
     }
     k_hysteresis<<<n, 1024, 65536, st>>>(edges, (u32 *)ctx->queue.p, (int *)ctx->counters.p, h, w);
     LE_T1(ctx, LE_K_HYST, st);
@@ -478,12 +480,14 @@ static int canny_thresholds(le_ctx *ctx, double lo, double hi, int *ilo, int *ih
 extern "C" int le_canny_u8(le_ctx *ctx, const uint8_t *src, uint8_t *edges, int n, int h, int w, double lo,
                            double hi, void *stream)
 {
+    LE_ON_DEVICE(ctx);
     return le_front_canny_u8(ctx, src, 1, 0, 0, edges, n, h, w, lo, hi, stream);
 }
 
 extern "C" int le_front_canny_u8(le_ctx *ctx, const uint8_t *src, int src_channels, int do_blur, int do_normalize,
                                  uint8_t *edges, int n, int h, int w, double lo, double hi, void *stream)
 {
+    LE_ON_DEVICE(ctx);
     int rc = check_img(ctx, src, edges, n, h, w);
     if (rc) return rc;
     LE_REQUIRE(ctx, src_channels == 1 || src_channels == 3, "src_channels must be 1 or 3");

@@ -715,7 +715,7 @@ static int launch_rows_t(le_ctx *ctx, const u8 *src, u8 *edges, int n, int h, in
     // enough warps to fill the machine even for one small frame, long segments for big batches
     long long target_warps = (long long)ctx->sm_count * 32;
     int rows = 160;
-    if (const char *e = getenv("LE_FRONT_ROWS")) rows = max(8, atoi(e));  // A/B measurements
+    if (const int e = LE_KNOB_INT("LE_FRONT_ROWS", 0)) rows = max(8, e);  // A/B measurements
     while (rows > 8 && (long long)n * A.nstrips * ((h + rows - 1) / rows) < target_warps) rows /= 2;
     A.rows_per_seg = rows;
     A.nsegs = (h + rows - 1) / rows;
@@ -725,7 +725,7 @@ static int launch_rows_t(le_ctx *ctx, const u8 *src, u8 *edges, int n, int h, in
     // in rows/2, the rest in rows/4 (each segment re-runs 8 warm-up rows, so short segments are only worth
     // it where they shorten the tail; measured best of 1..4 levels x 90..360 rows).  A small batch: one level.
     int nlv = (n >= 16 && rows >= 64) ? FR_LEVELS - 1 : 1;
-    if (const char *e = getenv("LE_FRONT_LEVELS")) nlv = max(1, min(FR_LEVELS, atoi(e)));  // A/B measurements
+    if (const int e = LE_KNOB_INT("LE_FRONT_LEVELS", 0)) nlv = max(1, min(FR_LEVELS, e));  // A/B measurements
     long long items = 0;
     int f0 = 0;
     for (int l = 0; l < FR_LEVELS; l++) {
@@ -741,13 +741,13 @@ static int launch_rows_t(le_ctx *ctx, const u8 *src, u8 *edges, int n, int h, in
     A.lvl_frame0[FR_LEVELS] = n;
     A.lvl_item0[FR_LEVELS] = (int)items;
     int per_sm = FR_MINBLK;
-    if (const char *e = getenv("LE_FRONT_BLOCKS_PER_SM")) per_sm = max(1, min(FR_MINBLK, atoi(e)));  // A/B measurements
+    if (const int e = LE_KNOB_INT("LE_FRONT_BLOCKS_PER_SM", 0)) per_sm = max(1, min(FR_MINBLK, e));  // A/B measurements
     dim3 grid((unsigned)min(items, (long long)ctx->sm_count * per_sm));
     LE_T0(ctx, LE_K_FRONT, st);
-    static bool carveout_set = false;  // all of the SM's shared memory: 24 one-warp blocks with their rings
-    if (!carveout_set) {
+    static le_dev_once carveout_set;  // all of the SM's shared memory: 24 one-warp blocks with their rings
+    if (carveout_set.needs(ctx->device, 1)) {
         cudaFuncSetAttribute(k_front_rows<BGR, BLUR, LUT, TMA>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-        carveout_set = true;
+        carveout_set.done(ctx->device, 1);
     }
     CUtensorMap tm;
     memset(&tm, 0, sizeof(tm));
@@ -778,7 +778,7 @@ int le_front_rows_launch(le_ctx *ctx, const u8 *src, int ch, int blur, int lut, 
     // Bulk (TMA) copies need 16-byte aligned sources and sizes: rows that are 16-byte multiples on a
     // 16-byte aligned base.  A ring row starts up to 12 bytes before the strip and ends up to 400 bytes
     // after its first byte, which must stay inside the frame for rows <= h - 3: w >= 160 covers it.
-    const bool tma = (w % 16) == 0 && w >= 160 && ((uintptr_t)src % 16) == 0 && !getenv("LE_FRONT_NO_TMA");
+    const bool tma = (w % 16) == 0 && w >= 160 && ((uintptr_t)src % 16) == 0 && !LE_KNOB_SET("LE_FRONT_NO_TMA");
     if (tma) return launch_rows_v<true>(ctx, src, ch, blur, lut, edges, n, h, w, lo, hi, st);
     return launch_rows_v<false>(ctx, src, ch, blur, lut, edges, n, h, w, lo, hi, st);
 }

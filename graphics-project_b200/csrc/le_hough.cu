@@ -420,6 +420,7 @@ k_hough_vote(const u32 *__restrict__ queue, int *__restrict__ counters, const fl
                                 if (there[r]) {
                                     int pos = atomicAdd(&cnt[LE_C_PEAKS], 1);
                                     if (pos < peak_cap) pk[pos] = key;
+                                    else cnt[LE_C_OVERFLOW] = 4;  // peak list full: le_check reports it
                                 } else {
                                     int pos = atomicAdd(&cnt[LE_C_AUX1], 1);
                                     if (pos < HV_CAND_CAP) cand[(size_t)f * HV_CAND_CAP + pos] = key;
@@ -476,6 +477,7 @@ k_hough_vote(const u32 *__restrict__ queue, int *__restrict__ counters, const fl
                             if (test_here) {
                                 int pos = atomicAdd(&cnt[LE_C_PEAKS], 1);
                                 if (pos < peak_cap) pk[pos] = key;
+                                else cnt[LE_C_OVERFLOW] = 4;
                             } else {
                                 int pos = atomicAdd(&cnt[LE_C_AUX1], 1);
                                 if (pos < HV_CAND_CAP) cand[(size_t)f * HV_CAND_CAP + pos] = key;
@@ -515,6 +517,7 @@ k_hough_vote(const u32 *__restrict__ queue, int *__restrict__ counters, const fl
                     int pos = atomicAdd(&cnt[LE_C_PEAKS], 1);
                     u32 idx = (u32)((r + 1) * rowlen + cc);
                     if (pos < peak_cap) pk[pos] = ((u64)(u32)v << 32) | (u64)(0xffffffffu - idx);
+                    else cnt[LE_C_OVERFLOW] = 4;
                 }
             };
             const int ncand = *(volatile int *)&cnt[LE_C_AUX1];
@@ -559,10 +562,10 @@ static int launch_vote(le_ctx *ctx, int n, int h, int w, int numangle, int numrh
                        int32_t *counts, int max_lines, cudaStream_t st)
 {
     size_t smem = (size_t)A * stride * 2;
-    static size_t attr = 0;
-    if (smem > attr) {
+    static le_dev_once attr;
+    if (attr.needs(ctx->device, smem)) {
         LE_CUDA(ctx, cudaFuncSetAttribute(k_hough_vote<A, HALO, H16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr = smem;
+        attr.done(ctx->device, smem);
     }
     constexpr int OUT = HALO ? A - 2 : A;
     int stripes = (numangle + OUT - 1) / OUT;
@@ -590,18 +593,27 @@ extern "C" int le_hough_lines(le_ctx *ctx, const uint8_t *edges, int n, int h, i
                               int threshold, int32_t *accum, float *lines, int32_t *votes, int32_t *counts,
                               int max_lines, void *stream)
 {
+    LE_ON_DEVICE(ctx);
     if (!ctx) return LE_ERR_INVALID;
     LE_REQUIRE(ctx, n > 0 && h > 0 && w > 0, "n, h, w must be positive");
     LE_REQUIRE(ctx, lines && counts && max_lines > 0, "lines/counts must be non-null, max_lines positive");
     LE_REQUIRE(ctx, rho > 0 && theta > 0, "rho and theta must be positive");
     LE_REQUIRE(ctx, (size_t)h * w < ((size_t)1 << 30), "frame too large");
     LE_REQUIRE(ctx, !accum || (((size_t)accum) & 3) == 0, "accum must be 4-byte aligned");
-    cudaSetDevice(ctx->device);
     cudaStream_t st = (cudaStream_t)stream;
     int numangle, numrho, stride;
     hough_dims_host(h, w, rho, theta, &numangle, &numrho);
     LE_REQUIRE(ctx, numangle >= 1 && numrho >= 1, "degenerate accumulator");
     LE_REQUIRE(ctx, (size_t)(numangle + 2) * (numrho + 2) < ((size_t)1 << 31), "accumulator too large");
+    {
+        // The stripe histogram counts in u16 and rounds with a magic-number add (exact for |v| < 2^22).  A bin
+        // collects at most the pixels of a strip (rho + 1) wide across the frame's diagonal (cv2 counts in
+        // int32 and has no such limit): parameter combinations beyond that are refused, not wrapped.
+        const double diag = sqrt((double)h * h + (double)w * w);
+        if ((ceil(rho) + 1) * (diag + 2) >= 65535.0 || (diag + 2) / (double)(float)rho >= 4194304.0)
+            return le_fail(ctx, LE_ERR_UNSUPPORTED, "rho = %g on a %d x %d frame exceeds the 16-bit vote counters "
+                           "or the exact rounding range of the Hough kernels", rho, w, h);
+    }
     int rc = le_edge_list_from_map(ctx, edges, n, h, w, st);
     if (rc) return rc;
     rc = le_hough_upload_trig(ctx, 0, h, w, rho, theta, numangle, &stride, st);
@@ -625,13 +637,12 @@ extern "C" int le_hough_lines(le_ctx *ctx, const uint8_t *edges, int n, int h, i
         if ((size_t)cand * stride * 2 <= two) A = cand;
     for (int cand = 32; cand >= 4 && !A; cand >>= 1)
         if ((size_t)cand * stride * 2 <= budget) A = cand;
-    if (const char *e = getenv("LE_VOTE_A")) {  // development knob: force the stripe height
-        const int v = atoi(e);
+    if (const int v = LE_KNOB_INT("LE_VOTE_A", 0)) {  // development knob: force the stripe height
         if ((v == 4 || v == 8 || v == 16 || v == 32) && (size_t)v * stride * 2 <= budget) A = v;
     }
     // without halo rows when the accumulator is written (the deferred boundary test reads it back)
     const bool nohalo = accum != nullptr && A >= 4;
-    static const int no_h16 = getenv("LE_VOTE_F32") ? 1 : 0;  // development knob: float2 staging everywhere
+    const bool no_h16 = LE_KNOB_SET("LE_VOTE_F32");  // development knob: float2 staging everywhere
     const bool h16 = h <= 2048 && w <= 2048 && !no_h16;
 #define LE_VOTE(AA, HH) (h16 ? launch_vote<AA, HH, true> : launch_vote<AA, HH, false>)(ctx, n, h, w, numangle, numrho, stride, threshold, accum, peak_cap, (float)rho, \
                                             (float)theta, lines, votes, counts, max_lines, st)

@@ -409,13 +409,20 @@ extern "C" int le_hough_lines_p(le_ctx *ctx, const uint8_t *edges, int n, int h,
                                 int threshold, int min_line_length, int max_line_gap, int32_t *segs,
                                 int32_t *counts, int max_segs, void *stream)
 {
+    LE_ON_DEVICE(ctx);
     if (!ctx) return LE_ERR_INVALID;
     LE_REQUIRE(ctx, edges && segs && counts, "null pointer");
     LE_REQUIRE(ctx, n > 0 && h > 0 && w > 0 && max_segs > 0, "n, h, w, max_segs must be positive");
     LE_REQUIRE(ctx, h < 65536 && w < 65536, "frame too large");
     LE_REQUIRE(ctx, rho > 0 && theta > 0, "rho and theta must be positive");
     LE_REQUIRE(ctx, max(h, w) + 64 <= PP_MAXT_WORDS * 32, "frame too large for the walk bitmap");
-    cudaSetDevice(ctx->device);
+    {
+        // 16-bit accumulator cells (biased u16 / short) and magic-number rounding: see le_hough_lines
+        const double diag = sqrt((double)h * h + (double)w * w);
+        if ((ceil(rho) + 1) * (diag + 2) >= 32767.0 || (diag + 2) / (double)(float)rho >= 4194304.0)
+            return le_fail(ctx, LE_ERR_UNSUPPORTED, "rho = %g on a %d x %d frame exceeds the 16-bit vote counters "
+                           "or the exact rounding range of the Hough kernels", rho, w, h);
+    }
     cudaStream_t st = (cudaStream_t)stream;
     int numangle, numrho, stride;
     le_hough_dims(h, w, rho, theta, &numangle, &numrho);
@@ -443,15 +450,15 @@ extern "C" int le_hough_lines_p(le_ctx *ctx, const uint8_t *edges, int n, int h,
                                                   (int *)ctx->counters.p, npx, nseg, w);
     }
     LE_LAUNCH_CHECK(ctx);
-    if (numangle <= 192 && !getenv("LE_PPHT_GENERIC"))  // batched kernel (le_houghp_fast.cu); same results
+    if (numangle <= 192 && !LE_KNOB_SET("LE_PPHT_GENERIC"))  // batched kernel (le_houghp_fast.cu); same results
         return le_ppht_fast_launch(ctx, n, h, w, numangle, stride, threshold, min_line_length, max_line_gap, segs,
                                    counts, max_segs, g_ppht_trace, g_ppht_trace_cap, st);
     LE_CUDA(ctx, cudaMemsetAsync(ctx->ppht_accum.p, 0, sizeof(u16) * (size_t)numangle * stride * n, st));
     LE_T1(ctx, LE_K_PPHT_PREP, st);
-    static bool attr = false;
-    if (!attr) {
+    static le_dev_once attr;
+    if (attr.needs(ctx->device, sizeof(PPShared))) {
         LE_CUDA(ctx, cudaFuncSetAttribute(k_ppht, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PPShared)));
-        attr = true;
+        attr.done(ctx->device, sizeof(PPShared));
     }
     LE_T0(ctx, LE_K_PPHT, st);
     k_ppht<<<n, PP_THREADS, sizeof(PPShared), st>>>((u8 *)ctx->ppht_mask.p, (u32 *)ctx->ppht_nz.p,

@@ -305,10 +305,10 @@ int le_ppht_fast_launch(le_ctx *ctx, int n, int h, int w, int numangle, int stri
     // accumulator: u16 cells biased by 0x4040 (byte pattern 0x40), two per word
     size_t bytes = sizeof(u16) * (size_t)numangle * stride * n;
     LE_CUDA(ctx, cudaMemsetAsync(ctx->ppht_accum.p, 0x40, bytes, st));
-    static bool attr = false;
-    if (!attr) {
+    static le_dev_once attr;
+    if (attr.needs(ctx->device, sizeof(PFShared))) {
         LE_CUDA(ctx, cudaFuncSetAttribute(k_ppht_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PFShared)));
-        attr = true;
+        attr.done(ctx->device, sizeof(PFShared));
     }
     LE_T1(ctx, LE_K_PPHT_PREP, st);
     LE_T0(ctx, LE_K_PPHT, st);

@@ -1453,6 +1453,7 @@ extern "C" int le_lsd(le_ctx *ctx, const uint8_t *gray, int n, int h, int w, int
                       float *segs, double *width, double *prec_out, double *nfa_out, int32_t *counts, int max_segs,
                       void *stream)
 {
+    LE_ON_DEVICE(ctx);
     if (!ctx) return LE_ERR_INVALID;
     LE_REQUIRE(ctx, gray && segs && counts, "null pointer");
     LE_REQUIRE(ctx, n > 0 && h > 1 && w > 1 && max_segs > 0, "n, h, w, max_segs must be positive");
@@ -1460,7 +1461,6 @@ extern "C" int le_lsd(le_ctx *ctx, const uint8_t *gray, int n, int h, int w, int
     LE_REQUIRE(ctx, scale > 0 && sigma_scale > 0 && quant >= 0 && ang_th > 0 && ang_th < 180, "bad LSD parameters");
     LE_REQUIRE(ctx, n_bins > 0 && n_bins <= 8192, "n_bins must be in 1..8192");
     if (refine < 0 || refine > 2) return le_fail(ctx, LE_ERR_UNSUPPORTED, "LSD refine=%d is not a cv2 mode", refine);
-    cudaSetDevice(ctx->device);
     cudaStream_t st = (cudaStream_t)stream;
     int H = h, W = w;
     le_lsd_scaled_dims(h, w, scale, &H, &W);
@@ -1472,7 +1472,7 @@ extern "C" int le_lsd(le_ctx *ctx, const uint8_t *gray, int n, int h, int w, int
     if ((rc = le_ensure(ctx, &ctx->lsd1, npx * n))) return rc;                                 // scaled image
     if ((rc = le_ensure(ctx, &ctx->lsd2, sizeof(u32) * npx * n))) return rc;                   // angles
     if ((rc = le_ensure(ctx, &ctx->lsd3, sizeof(u32) * npx * n))) return rc;                   // order
-    static const int spec = getenv("LE_LSD_SERIAL") ? 0 : 1;  // development knob: the one-warp-per-frame kernel
+    const int spec = LE_KNOB_SET("LE_LSD_SERIAL") ? 0 : 1;  // development knob: the one-warp-per-frame kernel
     if ((rc = le_ensure(ctx, &ctx->lsd4, sizeof(u32) * npx * n * (spec ? 2 : 1)))) return rc;  // region lists
     if (spec && (rc = le_ensure(ctx, &ctx->lsd7, sizeof(u32) * npx * n))) return rc;          // speculative tags
     if ((rc = le_ensure(ctx, &ctx->lsd6, sizeof(float2) * npx * n))) return rc;                // cos/sin of the angles
@@ -1495,7 +1495,7 @@ extern "C" int le_lsd(le_ctx *ctx, const uint8_t *gray, int n, int h, int w, int
         const bool wordwise = (w & 3) == 0 && (((size_t)gray) & 3) == 0 && (hh == 3 || hh == 5);
         // fused blur + resize: the largest destination tile whose samples fit the 128 x 32 shared tile
         int dtw = 0, dth = 0;
-        static const int unfused = getenv("LE_LSD_UNFUSED") ? 1 : 0;  // development knob: the two-kernel path
+        const int unfused = LE_KNOB_SET("LE_LSD_UNFUSED") ? 1 : 0;  // development knob: the two-kernel path
         if (wordwise && scale < 1 && !unfused) {
             auto fits = [](const std::vector<int2> &tab, int src, int dt, int cap, int align) {
                 for (int d0 = 0; d0 < (int)tab.size(); d0 += dt) {
@@ -1584,14 +1584,14 @@ extern "C" int le_lsd(le_ctx *ctx, const uint8_t *gray, int n, int h, int w, int
         // warps per frame: 16 while every frame can have an SM of its own, else 8 (four CTAs per SM, 64 registers):
         // a second wave of CTAs costs more than the narrower rounds
         int K = n <= ctx->sm_count ? 16 : 8;
-        if (const char *e = getenv("LE_LSD_K")) K = atoi(e) == 8 ? 8 : (atoi(e) == 16 ? 16 : K);  // development knob
+        if (const int e = LE_KNOB_INT("LE_LSD_K", 0)) K = e == 8 ? 8 : (e == 16 ? 16 : K);  // development knob
         const int sg_smem = K * (LSD_RING + SG_HASH) * (int)sizeof(u32);
-        static bool sg_attr = false;
-        if (!sg_attr) {
+        static le_dev_once sg_attr;
+        if (sg_attr.needs(ctx->device, 1)) {
             const int big = 16 * (LSD_RING + SG_HASH) * (int)sizeof(u32);
             LE_CUDA(ctx, cudaFuncSetAttribute(k_lsd_grow_spec<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
             LE_CUDA(ctx, cudaFuncSetAttribute(k_lsd_grow_spec<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-            sg_attr = true;
+            sg_attr.done(ctx->device, 1);
         }
 #define LE_GROW(KK, AA)                                                                                          \
     k_lsd_grow_spec<KK, AA><<<n, KK * 32, sg_smem, st>>>(img, (u32 *)ctx->lsd2.p, (u32 *)ctx->lsd7.p,               \

@@ -204,12 +204,12 @@ extern "C" int le_combine_parallel_lines(le_ctx *ctx, const double *segs, const 
                                          double default_cos, double *out_segs, int32_t *out_src, int32_t *out_counts,
                                          void *stream)
 {
+    LE_ON_DEVICE(ctx);
     if (!ctx) return LE_ERR_INVALID;
     LE_REQUIRE(ctx, segs && out_segs && out_counts, "null pointer");
     LE_REQUIRE(ctx, n > 0 && max_k > 0, "n and max_k must be positive");
     LE_REQUIRE(ctx, segs != out_segs, "le_combine_parallel_lines is not in-place");
     if (max_k > MG_MAX) return le_fail(ctx, LE_ERR_UNSUPPORTED, "at most %d segments per frame (got %d)", MG_MAX, max_k);
-    cudaSetDevice(ctx->device);
     cudaStream_t st = (cudaStream_t)stream;
     const int nw = (max_k + 31) / 32;
     int rc = le_ensure(ctx, &ctx->misc, sizeof(u32) * (size_t)n * max_k * nw);

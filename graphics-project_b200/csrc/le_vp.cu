@@ -441,12 +441,12 @@ __global__ void __launch_bounds__(VPF_THREADS) k_vp_fit(const double *__restrict
 static int vp_common(le_ctx *ctx)
 {
     if (!ctx) return LE_ERR_INVALID;
-    cudaSetDevice(ctx->device);
     return LE_OK;
 }
 
 extern "C" int le_segments_to_polar(le_ctx *ctx, const double *segs, int m, double *polar, void *stream)
 {
+    LE_ON_DEVICE(ctx);
     int rc = vp_common(ctx);
     if (rc) return rc;
     LE_REQUIRE(ctx, segs && polar && m > 0, "bad arguments");
@@ -458,6 +458,7 @@ extern "C" int le_segments_to_polar(le_ctx *ctx, const double *segs, int m, doub
 extern "C" int le_vp_loss(le_ctx *ctx, const double *lines, int m, const double *cand, int k, double width,
                           double height, double *loss, void *stream)
 {
+    LE_ON_DEVICE(ctx);
     int rc = vp_common(ctx);
     if (rc) return rc;
     LE_REQUIRE(ctx, lines && cand && loss && m > 0 && k > 0, "bad arguments");
@@ -469,6 +470,7 @@ extern "C" int le_vp_loss(le_ctx *ctx, const double *lines, int m, const double 
 extern "C" int le_vp_sphere_hist(le_ctx *ctx, const double *segs, int m, double width, double height, int32_t *hist,
                                  int n_az, int n_el, void *stream)
 {
+    LE_ON_DEVICE(ctx);
     int rc = vp_common(ctx);
     if (rc) return rc;
     LE_REQUIRE(ctx, segs && hist && m >= 0 && n_az > 0 && n_el > 0, "bad arguments");
@@ -484,6 +486,7 @@ extern "C" int le_vp_sphere_hist(le_ctx *ctx, const double *segs, int m, double 
 extern "C" int le_pair_intersections(le_ctx *ctx, const float *lines, int m, double *out, int32_t *count, int max_out,
                                      void *stream)
 {
+    LE_ON_DEVICE(ctx);
     int rc = vp_common(ctx);
     if (rc) return rc;
     LE_REQUIRE(ctx, lines && out && count && m >= 0 && max_out > 0, "bad arguments");
@@ -507,6 +510,7 @@ extern "C" int le_pair_intersections(le_ctx *ctx, const float *lines, int m, dou
 extern "C" int le_polar_batch(le_ctx *ctx, const float *segs, const int32_t *counts, int n, int max_segs,
                               double min_len, double *polar, int32_t *pcounts, void *stream)
 {
+    LE_ON_DEVICE(ctx);
     int rc = vp_common(ctx);
     if (rc) return rc;
     LE_REQUIRE(ctx, segs && counts && polar && pcounts && n > 0 && max_segs > 0, "bad arguments");
@@ -520,6 +524,7 @@ extern "C" int le_vp_fit_batch(le_ctx *ctx, const double *polar, const int32_t *
                                double width, double height, int n_phi, int n_th, int n_ref, int rounds,
                                double ref_area, int32_t *hist, int n_az, int n_el, int top, double *fit, void *stream)
 {
+    LE_ON_DEVICE(ctx);
     int rc = vp_common(ctx);
     if (rc) return rc;
     LE_REQUIRE(ctx, polar && pcounts && fit && n > 0 && max_lines > 0, "bad arguments");

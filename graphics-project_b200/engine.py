@@ -72,8 +72,23 @@ class Engine:
                 raise ValueError("expected [N,H,W]")
         return t.contiguous()
 
+    def _out(self, t, shape, dtype, name):
+        """A caller-provided output goes to the kernels as a raw pointer: it must be exactly what they write."""
+        if t is None:
+            return None
+        if not (isinstance(t, torch.Tensor) and t.is_cuda and t.device == self.device):
+            raise TypeError(f"{name}: expected a CUDA tensor on {self.device}")
+        if t.dtype != dtype:
+            raise TypeError(f"{name}: expected dtype {dtype}, got {t.dtype}")
+        if tuple(t.shape) != tuple(shape):
+            raise ValueError(f"{name}: expected shape {tuple(shape)}, got {tuple(t.shape)}")
+        if not t.is_contiguous():
+            raise ValueError(f"{name}: must be contiguous")
+        return t
+
     def check(self):
-        """Synchronise and raise if a device-side queue overflowed."""
+        """Synchronise and raise if a device-side queue overflowed (edge queues, Hough peak list: a frame whose
+        ``counts`` exceeds the peak capacity max(4 * max_lines, 65536) is reported here, its lines are unreliable)."""
         self._ok(lib.le_check(self._ctx, self._stream()))
 
     @property
@@ -122,13 +137,23 @@ class Engine:
     def canny(self, gray, lo, hi, out=None):
         return self.front_canny(gray, lo, hi, blur=False, normalize=False, out=out)
 
-    def front_canny(self, src, lo, hi, blur=False, normalize=False, out=None):
-        """[BGR->gray] -> [blur5] -> [normalize] -> Canny.  ``src`` is [N,H,W,3] BGR or [N,H,W] gray."""
-        ch = 3 if src.dim() == 4 else 1  # a single BGR frame must be passed as [1,H,W,3]
+    def front_canny(self, src, lo, hi, blur=False, normalize=False, out=None, channels=None):
+        """[BGR->gray] -> [blur5] -> [normalize] -> Canny.  ``src`` is [N,H,W,3] BGR or [N,H,W] gray (or one gray
+        frame [H,W]).  A 3-D tensor whose last dimension is 3 is ambiguous (one BGR frame, or H gray frames three
+        pixels wide) and is refused unless ``channels`` says which."""
+        if channels is None:
+            if src.dim() == 3 and src.shape[-1] == 3:
+                raise ValueError("front_canny: a [.,.,3] tensor is ambiguous -- pass one BGR frame as [1,H,W,3], "
+                                 "or say channels=1 / channels=3")
+            channels = 3 if src.dim() == 4 else 1
+        if channels not in (1, 3):
+            raise ValueError("channels must be 1 or 3")
+        ch = channels
         src = self._img(src, ch)
         n, h, w = src.shape[:3]
         if out is None:
             out = torch.empty((n, h, w), dtype=torch.uint8, device=self.device)
+        self._out(out, (n, h, w), torch.uint8, "front_canny out")
         self._ok(lib.le_front_canny_u8(self._ctx, _ptr(src), ch, int(blur), int(normalize), _ptr(out), n, h, w,
                                        float(lo), float(hi), self._stream()))
         self._last_edges_shape = (n, h, w)
@@ -208,6 +233,7 @@ class Engine:
         base, off, (sn, sy, sx, sc), (n, h, w) = self._f32_strided(src)
         if out is None:
             out = torch.empty((n, h, w), dtype=torch.uint8, device=self.device)
+        self._out(out, (n, h, w), torch.uint8, "f32_front_canny out")
         self._ok(lib.le_f32_front_canny(self._ctx, C.c_void_p(base.data_ptr() + 4 * off), sn, sy, sx, sc, _ptr(out),
                                         n, h, w, float(lo), float(hi), self._stream()))
         self._last_edges_shape = (n, h, w)
@@ -234,6 +260,12 @@ class Engine:
         na, nr = self.hough_dims(h, w, rho, theta)
         if out is not None:
             lines, votes, counts, accum = out
+            if not (isinstance(lines, torch.Tensor) and lines.dim() == 3):
+                raise ValueError("hough_lines out: lines must be [N, max_lines, 2]")
+            self._out(lines, (n, lines.shape[1], 2), torch.float32, "hough_lines out: lines")
+            self._out(votes, (n, lines.shape[1]), torch.int32, "hough_lines out: votes")
+            self._out(counts, (n,), torch.int32, "hough_lines out: counts")
+            self._out(accum, (n, na + 2, nr + 2), torch.int32, "hough_lines out: accum")
         else:
             lines = torch.empty((n, max_lines, 2), dtype=torch.float32, device=self.device)
             votes = torch.empty((n, max_lines), dtype=torch.int32, device=self.device) if want_votes else None

@@ -140,7 +140,31 @@ def regress_lines(lines, iterations=500, refinement_iterations=100, refinement_a
                   height=HEIGHT, verbose=True, use_seeds=True):
     """opencv_fit_color.py:28-47 signature and return type; deterministic GPU search.
 
-    ``iterations`` / ``refinement_iterations`` are lower bounds on the number of candidates per phase."""
+    One launch chain and one 24-byte read-back: the frame goes through the batched kernels (``le_vp_fit_batch``
+    with n = 1 -- sphere histogram, seeds, grid and refinement boxes in one CTA), the same candidates in the same
+    order as ``regress_lines_stepwise``.  ``iterations`` / ``refinement_iterations`` are lower bounds on the
+    number of candidates per phase."""
+    lines = np.asarray(lines, dtype=np.float64).reshape(-1, 2)
+    if len(lines) == 0:
+        raise ZeroDivisionError("division by zero")  # min_loss divides by len(lines) in the reference
+    eng = default_engine()
+    polar = torch.from_numpy(np.ascontiguousarray(lines))[None].to(eng.device)
+    pcounts = torch.tensor([len(lines)], dtype=torch.int32, device=eng.device)
+    fit, _ = regress_lines_batch(polar, pcounts, iterations, refinement_iterations, refinement_area, width, height,
+                                 want_hist=bool(use_seeds), engine=eng)
+    phi, theta, best_loss = (float(v) for v in fit[0].cpu().numpy())
+    best = (phi, theta) if best_loss < 100000 else (0, 0)
+    if best_loss >= 100000:
+        best_loss = 100000
+    if verbose:
+        print(" The loss is ", best_loss)
+    return best, best_loss
+
+
+def regress_lines_stepwise(lines, iterations=500, refinement_iterations=100, refinement_area=0.3, width=WIDTH,
+                  height=HEIGHT, verbose=True, use_seeds=True):
+    """The search of ``regress_lines`` phase by phase from the host (``le_vp_loss`` per candidate set, five round
+    trips): kept as the cross-check of the fused kernel (tests/test_gpu_lines_batch.py), not used by the wrappers."""
     lines = np.asarray(lines, dtype=np.float64).reshape(-1, 2)
     best_loss = 100000
     best = (0, 0)

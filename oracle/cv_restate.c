@@ -7,7 +7,7 @@
  * `opencv-python==4.10.0.84` (reference requirements.txt:2), whose source is NOT
  * under /root/reference.  The algorithms below restate the published OpenCV
  * algorithms (imgproc: color, smooth, canny, hough, lsd) and are PINNED against
- * the cv2 4.13.0 wheel that ships in this image (tests/test_oracle_vs_cv2.py)
+ * the cv2 4.13.0 wheel that ships in this image (tests/test_oracle.py::test_oracle_vs_live_cv2)
  * and against golden vectors generated from the reference's own fixture images
  * (tests/golden/, made by tests/golden/make_golden.py).
  *

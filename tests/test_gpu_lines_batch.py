@@ -64,7 +64,7 @@ def test_vp_fit_batch_equals_stepwise_search(engine, golden_vp, lsd_batch):
     for i, lines in enumerate(sets):
         if len(lines) == 0:
             continue
-        (phi, theta), loss = vp.regress_lines(lines, 1000, 500, np.deg2rad(15), verbose=False, use_seeds=False)
+        (phi, theta), loss = vp.regress_lines_stepwise(lines, 1000, 500, np.deg2rad(15), verbose=False, use_seeds=False)
         assert fit[i, 2] == pytest.approx(loss, rel=1e-9), i
         assert fit[i, 0] == pytest.approx(phi, abs=1e-9) and fit[i, 1] == pytest.approx(theta, abs=1e-9), i
         assert ref_sum_loss(fit[i, 0], fit[i, 1], lines) == pytest.approx(fit[i, 2], rel=1e-9)
@@ -82,8 +82,11 @@ def test_vp_fit_batch_with_sphere_seeds(engine, golden_vp):
     runs = golden_vp["regress_runs_lsd"]
     assert ref_sum_loss(fit[0, 0], fit[0, 1], lines) == pytest.approx(fit[0, 2], rel=1e-9)
     assert fit[0, 2] <= np.median(runs[:, 2])
-    _, loss = vp.regress_lines(lines, 1000, 500, np.deg2rad(15), verbose=False)
+    _, loss = vp.regress_lines_stepwise(lines, 1000, 500, np.deg2rad(15), verbose=False)
     assert fit[0, 2] <= loss * 1.02
+    # the single-frame wrapper IS the batch kernel with n = 1: identical result
+    (phi1, th1), loss1 = vp.regress_lines(lines, 1000, 500, np.deg2rad(15), verbose=False)
+    assert (phi1, th1, loss1) == tuple(fit[0])
     for i, ls in enumerate((lines, lines[::2])):
         m = len(ls)
         rho, phi = ls[:, 0], ls[:, 1]
@@ -107,5 +110,5 @@ def test_get_camera_angles_batch(engine, lsd_batch):
         lines = polar[f, :int(pcounts[f])].cpu().numpy()
         assert 0 <= fit[f, 0] < np.pi + 0.3 and -0.3 <= fit[f, 1] < np.pi / 2 + 0.3
         assert ref_sum_loss(fit[f, 0], fit[f, 1], lines) == pytest.approx(fit[f, 2], rel=1e-9)
-        _, loss = vp.regress_lines(lines, 1000, 500, 0.3, verbose=False)
+        _, loss = vp.regress_lines_stepwise(lines, 1000, 500, 0.3, verbose=False)
         assert fit[f, 2] <= loss * 1.02
