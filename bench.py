@@ -424,11 +424,14 @@ class EngineRun:
     def gather_args(self):
         return self.counts, self.payload
 
-    def pipeline(self, chunk=None):
-        wl, P, d = self.wl, self.gp.pipeline, self.dev.index
-        torch = self.torch
+    MAX_K = {CannyHough.name: 1024, CannyHoughP.name: 1024, Lsd.name: 2048, LinesVp.name: 2048}
+
+    @staticmethod
+    def pipeline(wl, gp, torch, dev, B, chunk=None):
+        """(host pipeline, pinned output tensors, class name) of the workload's chain."""
+        P, d = gp.pipeline, dev.index
         pin = lambda *s, dt: torch.empty(s, dtype=dt, pin_memory=True)  # noqa: E731
-        B, k = self.B, self.max_k
+        k = EngineRun.MAX_K[wl.name]
         if wl.name == CannyHough.name:
             return (P.CannyHoughHost(wl.h, wl.w, d, chunk=chunk or 32, max_lines=k, lo=wl.LO, hi=wl.HI, blur=True,
                                      threshold=wl.THR),
@@ -618,8 +621,7 @@ def run_engine(args, wl, rank, world, local_rank):
     if not args.no_e2e:
         del run
         torch.cuda.empty_cache()
-        run2 = EngineRun(wl, gp, torch, dev, frames[:0], 1)
-        pipe, outs, api = run2.pipeline(args.chunk)
+        pipe, outs, api = EngineRun.pipeline(wl, gp, torch, dev, B, args.chunk)
         for _ in range(2):
             pipe.run(host_frames, *outs)
         barrier()
@@ -636,8 +638,9 @@ def run_engine(args, wl, rank, world, local_rank):
         for _ in range(ceil_steps):
             for ci, c0 in enumerate(range(0, B, pipe.chunk)):
                 c1 = min(B, c0 + pipe.chunk)
-                with torch.cuda.stream(pipe.streams[ci & 1]):
-                    pipe.bufs[ci & 1]["src"][:c1 - c0].copy_(host_frames[c0:c1], non_blocking=True)
+                si = ci % len(pipe.streams)
+                with torch.cuda.stream(pipe.streams[si]):
+                    pipe.bufs[si]["src"][:c1 - c0].copy_(host_frames[c0:c1], non_blocking=True)
             torch.cuda.synchronize()
         dt_copy = (time.perf_counter() - t0) / ceil_steps
         if world > 1:

@@ -46,9 +46,11 @@ struct le_ctx {
     le_buf peaks;       // u64   [n][peak_cap]
     le_buf trig;        // float [2][numangle] + int [numangle] (rlo)
     le_buf tmp0, tmp1;  // generic images
-    le_buf ppht_accum, ppht_mask, ppht_nz;
+    le_buf ppht_accum, ppht_mask, ppht_nz, ppht_rng;
+    size_t ppht_rng_n;  // entries of the cv::RNG(-1) output table in ppht_rng
     le_buf lsd0, lsd1, lsd2, lsd3, lsd4, lsd5, lsd6, lsd7, lsd_tab;
     double lsd_key[4];
+    int lsd_epoch;  // call counter carried by the speculative grower's tags (le_lsd.cu)
     le_buf misc;
     // state shared between le_front_canny_u8 and le_hough_lines
     const void *edge_list_for;  // edges pointer the queue currently describes (or null)

@@ -79,7 +79,7 @@ extern "C" int le_destroy(le_ctx *ctx)
     LE_ON_DEVICE(ctx);
     cudaDeviceSynchronize();
     le_buf *bufs[] = {&ctx->counters, &ctx->queue, &ctx->lut, &ctx->peaks, &ctx->trig, &ctx->tmp0, &ctx->tmp1,
-                      &ctx->ppht_accum, &ctx->ppht_mask, &ctx->ppht_nz, &ctx->lsd0, &ctx->lsd1, &ctx->lsd2,
+                      &ctx->ppht_accum, &ctx->ppht_mask, &ctx->ppht_nz, &ctx->ppht_rng, &ctx->lsd0, &ctx->lsd1, &ctx->lsd2,
                       &ctx->lsd3, &ctx->lsd4, &ctx->lsd5, &ctx->lsd6, &ctx->lsd7, &ctx->lsd_tab, &ctx->misc};
     for (le_buf *b : bufs)
         if (b->p) cudaFree(b->p);

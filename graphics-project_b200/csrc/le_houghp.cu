@@ -14,6 +14,8 @@
 int le_ppht_fast_launch(le_ctx *ctx, int n, int h, int w, int numangle, int stride, int threshold, int min_len,
                         int max_gap, int32_t *segs, int32_t *counts, int max_segs, int32_t *trace, int trace_cap,
                         cudaStream_t st);
+int le_ppht_rounds_launch(le_ctx *ctx, int n, int h, int w, int numangle, int stride, int threshold, int min_len,
+                          int max_gap, int32_t *segs, int32_t *counts, int max_segs, cudaStream_t st);
 int le_hough_upload_trig(le_ctx *ctx, int kind, int h, int w, double rho, double theta, int numangle, int *stride_out,
                          cudaStream_t st);
 
@@ -450,6 +452,11 @@ extern "C" int le_hough_lines_p(le_ctx *ctx, const uint8_t *edges, int n, int h,
                                                   (int *)ctx->counters.p, npx, nseg, w);
     }
     LE_LAUNCH_CHECK(ctx);
+    // rounds of 64 picks over a precomputed visiting order (le_houghp_rounds.cu); LE_PPHT_ROUNDS=0 keeps the
+    // round-1 kernel (also used when a trace is requested); same results from all three
+    if (numangle <= 192 && !LE_KNOB_SET("LE_PPHT_GENERIC") && LE_KNOB_INT("LE_PPHT_ROUNDS", 1) && !g_ppht_trace)
+        return le_ppht_rounds_launch(ctx, n, h, w, numangle, stride, threshold, min_line_length, max_line_gap, segs,
+                                     counts, max_segs, st);
     if (numangle <= 192 && !LE_KNOB_SET("LE_PPHT_GENERIC"))  // batched kernel (le_houghp_fast.cu); same results
         return le_ppht_fast_launch(ctx, n, h, w, numangle, stride, threshold, min_line_length, max_line_gap, segs,
                                    counts, max_segs, g_ppht_trace, g_ppht_trace_cap, st);

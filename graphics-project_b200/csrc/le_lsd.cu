@@ -501,6 +501,13 @@ static __device__ __forceinline__ u32 ld_ca(const volatile u32 *p)
 }
 #define LSD_RING 256  // most recent region points, kept in shared memory for the BFS front
 
+// BFS trips take up to LSD_FRONT queued pixels at once: lanes 0-8 hold the neighbours of queue entry i, lanes 9-17
+// those of entry i + 1, lanes 18-26 those of entry i + 2, all fetched in ONE memory round trip (the growth is a
+// chain of dependent round trips, one per queue entry before).  The entries are then processed one after the
+// other exactly as the sequential scan would: a neighbour accepted while an earlier entry of the trip was
+// processed is struck from the later entries' candidates by comparing coordinates (its USED flag was loaded
+// before it was set), so the order of acceptance and the running region angle are unchanged.
+#define LSD_FRONT 3
 static __device__ int lsd_grow(volatile u32 *an, const float2 *__restrict__ cs, u32 *reg, u32 *ring, int W, int H, int sx, int sy, double tol,
                                double *reg_angle_out, int lane)
 {
@@ -516,38 +523,52 @@ static __device__ int lsd_grow(volatile u32 *an, const float2 *__restrict__ cs, 
     n = 1;
     float sumdx = (float)cos(reg_angle), sumdy = (float)sin(reg_angle);
     __syncwarp();
-    const int ky = lane / 3 - 1, kx = lane % 3 - 1;
-    for (int i = 0; i < n; i++) {
+    const int g = lane / 9, kk = lane - 9 * g;  // queue entry of the trip, neighbour of that entry
+    const int ky = kk / 3 - 1, kx = kk % 3 - 1;
+    for (int i = 0; i < n;) {
+        const int m = min(LSD_FRONT, n - i);
         // BFS front: the queue tail is almost always within the shared ring
-        u32 pt = (n - i <= LSD_RING) ? ((volatile u32 *)ring)[i & (LSD_RING - 1)] : ((volatile u32 *)reg)[i];
-        int px = (int)(pt & 0xffff), py = (int)(pt >> 16);
-        int xx = px + kx, yy = py + ky;
+        int px = 0, py = 0;
         u32 v = LSD_NOTDEF;
         float2 csn = make_float2(0.f, 0.f);
-        if (lane < 9 && xx >= 0 && xx < W && yy >= 0 && yy < H) {
+        if (g < m) {
+            const int qi = i + g;
+            const u32 pt = (n - qi <= LSD_RING) ? ((volatile u32 *)ring)[qi & (LSD_RING - 1)] : ((volatile u32 *)reg)[qi];
+            px = (int)(pt & 0xffff);
+            py = (int)(pt >> 16);
+        }
+        const int xx = px + kx, yy = py + ky;
+        if (g < m && xx >= 0 && xx < W && yy >= 0 && yy < H) {
             v = ld_ca(an + (size_t)yy * W + xx);
             csn = __ldg(cs + (size_t)yy * W + xx);  // read-only plane; garbage where the angle is undefined (never used)
         }
-        // visit only the neighbours that are defined and free, in (yy, xx) scan order
-        u32 candm = __ballot_sync(~0u, v != LSD_NOTDEF && !(v & LSD_USED)) & 0x1ffu;
-        while (candm) {
-            const int k = __ffs(candm) - 1;
-            candm &= candm - 1;
-            u32 vk = __shfl_sync(~0u, v, k);
-            double a = (double)__uint_as_float(vk) * D2R;
-            if (!aligned_to(reg_angle, a, tol)) continue;
-            int ax = px + (k % 3) - 1, ay = py + (k / 3) - 1;
-            if (lane == 0) {
-                u32 e = ((u32)ay << 16) | (u32)ax;
-                an[(size_t)ay * W + ax] = vk | LSD_USED;
-                reg[n] = e;
-                ring[n & (LSD_RING - 1)] = e;
+        bool avail = v != LSD_NOTDEF && !(v & LSD_USED);
+        for (int gg = 0; gg < m; gg++) {
+            // visit only the neighbours that are defined and free, in (yy, xx) scan order
+            u32 candm = (__ballot_sync(~0u, avail) >> (9 * gg)) & 0x1ffu;
+            const int cpx = __shfl_sync(~0u, px, 9 * gg), cpy = __shfl_sync(~0u, py, 9 * gg);
+            while (candm) {
+                const int k = __ffs(candm) - 1;
+                candm &= candm - 1;
+                const int src = 9 * gg + k;
+                u32 vk = __shfl_sync(~0u, v, src);
+                double a = (double)__uint_as_float(vk) * D2R;
+                if (!aligned_to(reg_angle, a, tol)) continue;
+                int ax = cpx + (k % 3) - 1, ay = cpy + (k / 3) - 1;
+                if (lane == 0) {
+                    u32 e = ((u32)ay << 16) | (u32)ax;
+                    an[(size_t)ay * W + ax] = vk | LSD_USED;
+                    reg[n] = e;
+                    ring[n & (LSD_RING - 1)] = e;
+                }
+                n++;
+                sumdx += __shfl_sync(~0u, csn.x, src);
+                sumdy += __shfl_sync(~0u, csn.y, src);
+                reg_angle = (double)d_fast_atan2(sumdy, sumdx) * D2R;
+                if (xx == ax && yy == ay) avail = false;  // also a neighbour of a later entry of this trip
             }
-            n++;
-            sumdx += __shfl_sync(~0u, csn.x, k);
-            sumdy += __shfl_sync(~0u, csn.y, k);
-            reg_angle = (double)d_fast_atan2(sumdy, sumdx) * D2R;
         }
+        i += m;
         __syncwarp();
     }
     *reg_angle_out = reg_angle;
@@ -984,6 +1005,7 @@ __device__ int g_lsd_stats[16];
 __device__ long long g_lsd_cyc[8];
 #endif
 #define SG_ENT 96  // free seeds examined per round (slots + deferred)
+#define SG_ROUND_LIM ((1u << 20) - 1)  // rounds that still fit the tag
 struct SgSlot {
     u32 seed;     // pixel index of the seed
     int ord_idx;  // its position in the ordered list
@@ -1028,25 +1050,31 @@ static __device__ int lsd_grow_spec(volatile u32 *an, volatile u32 *own, const f
     n = 1;
     float sumdx = (float)cos(reg_angle), sumdy = (float)sin(reg_angle);
     __syncwarp();
-    const int ky = lane / 3 - 1, kx = lane % 3 - 1;
+    const int g = lane / 9, kk = lane - 9 * g;  // queue entry of the trip, neighbour of that entry (see lsd_grow)
+    const int ky = kk / 3 - 1, kx = kk % 3 - 1;
     bool full = false;
-    for (int i = 0; i < n && !full; i++) {
-        u32 pt = (n - i <= LSD_RING) ? ((volatile u32 *)ring)[i & (LSD_RING - 1)] : ((volatile u32 *)reg)[i];
-        int px = (int)(pt & 0xffff), py = (int)(pt >> 16);
-        int xx = px + kx, yy = py + ky;
+    for (int i = 0; i < n && !full;) {
+        const int m = min(LSD_FRONT, n - i);
+        int px = 0, py = 0;
+        if (g < m) {
+            const int qi = i + g;
+            const u32 pt = (n - qi <= LSD_RING) ? ((volatile u32 *)ring)[qi & (LSD_RING - 1)] : ((volatile u32 *)reg)[qi];
+            px = (int)(pt & 0xffff);
+            py = (int)(pt >> 16);
+        }
+        const int xx = px + kx, yy = py + ky;
         u32 v = LSD_NOTDEF, o = 0;
         float2 csn = make_float2(0.f, 0.f);
-        if (lane < 9 && xx >= 0 && xx < W && yy >= 0 && yy < H) {
+        if (g < m && xx >= 0 && xx < W && yy >= 0 && yy < H) {
             v = ld_ca(an + (size_t)yy * W + xx);
             o = ld_ca(own + (size_t)yy * W + xx);
             csn = __ldg(cs + (size_t)yy * W + xx);
         }
-        const bool avail = v != LSD_NOTDEF && !(v & LSD_USED);
+        bool avail = v != LSD_NOTDEF && !(v & LSD_USED);
         const bool cur = o != 0 && ((o - 1u) >> 5) == round;
         const int oid = (int)((o - 1u) & 31u);
         const bool taken = cur && oid <= wid;  // mine already, or an earlier region of this round
         relied |= __reduce_or_sync(~0u, (avail && cur && oid < wid) ? (1u << oid) : 0u);
-        u32 candm = __ballot_sync(~0u, avail && !taken) & 0x1ffu;
         // A tag of a HIGHER id says nothing about this region: that warp may have overwritten this region's own
         // tag (plain stores race).  The region's exact pixel set (shared-memory hash) settles it.
         bool mine = false;
@@ -1058,29 +1086,36 @@ static __device__ int lsd_grow_spec(volatile u32 *an, volatile u32 *own, const f
                 if (t == 0xFFFFFFFFu) break;
             }
         }
-        candm &= ~__ballot_sync(~0u, mine);
-        while (candm) {
-            const int k = __ffs(candm) - 1;
-            candm &= candm - 1;
-            u32 vk = __shfl_sync(~0u, v, k);
-            double a = (double)__uint_as_float(vk) * D2R;
-            if (!aligned_to(reg_angle, a, tol)) continue;
-            if (n >= reg_cap || n >= SG_HASH_CAP) { full = true; break; }
-            int ax = px + (k % 3) - 1, ay = py + (k / 3) - 1;
-            if (lane == 0) {
-                u32 e = ((u32)ay << 16) | (u32)ax;
-                own[(size_t)ay * W + ax] = tag;
-                reg[n] = e;
-                ring[n & (LSD_RING - 1)] = e;
-                u32 hx = sg_hash(e);
-                while (hset[hx] != 0xFFFFFFFFu) hx = (hx + 1) & (SG_HASH - 1);
-                hset[hx] = e;
+        avail = avail && !taken && !mine;
+        for (int gg = 0; gg < m && !full; gg++) {
+            u32 candm = (__ballot_sync(~0u, avail) >> (9 * gg)) & 0x1ffu;
+            const int cpx = __shfl_sync(~0u, px, 9 * gg), cpy = __shfl_sync(~0u, py, 9 * gg);
+            while (candm) {
+                const int k = __ffs(candm) - 1;
+                candm &= candm - 1;
+                const int src = 9 * gg + k;
+                u32 vk = __shfl_sync(~0u, v, src);
+                double a = (double)__uint_as_float(vk) * D2R;
+                if (!aligned_to(reg_angle, a, tol)) continue;
+                if (n >= reg_cap || n >= SG_HASH_CAP) { full = true; break; }
+                int ax = cpx + (k % 3) - 1, ay = cpy + (k / 3) - 1;
+                if (lane == 0) {
+                    u32 e = ((u32)ay << 16) | (u32)ax;
+                    own[(size_t)ay * W + ax] = tag;
+                    reg[n] = e;
+                    ring[n & (LSD_RING - 1)] = e;
+                    u32 hx = sg_hash(e);
+                    while (hset[hx] != 0xFFFFFFFFu) hx = (hx + 1) & (SG_HASH - 1);
+                    hset[hx] = e;
+                }
+                n++;
+                sumdx += __shfl_sync(~0u, csn.x, src);
+                sumdy += __shfl_sync(~0u, csn.y, src);
+                reg_angle = (double)d_fast_atan2(sumdy, sumdx) * D2R;
+                if (xx == ax && yy == ay) avail = false;  // also a neighbour of a later entry of this trip
             }
-            n++;
-            sumdx += __shfl_sync(~0u, csn.x, k);
-            sumdy += __shfl_sync(~0u, csn.y, k);
-            reg_angle = (double)d_fast_atan2(sumdy, sumdx) * D2R;
         }
+        i += m;
         __syncwarp();
     }
     *reg_angle_out = reg_angle;
@@ -1098,7 +1133,7 @@ __global__ void __launch_bounds__(SG_K * 32, SG_K == 8 ? 4 : 1) k_lsd_grow_spec(
                                                              const int *__restrict__ counters, LsdParams P,
                                                              float *__restrict__ segs, double *__restrict__ widths,
                                                              double *__restrict__ precs, double *__restrict__ nfas,
-                                                             int32_t *__restrict__ counts)
+                                                             int32_t *__restrict__ counts, u32 epoch)
 {
     const int f = blockIdx.x, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int W = P.W, H = P.H;
@@ -1129,6 +1164,10 @@ __global__ void __launch_bounds__(SG_K * 32, SG_K == 8 ? 4 : 1) k_lsd_grow_spec(
     long long t_sel = 0, t_grow = 0, t_com = 0, t0 = 0;
 #endif
     for (u32 round = 0;; round++) {
+        // tags carry (call epoch, round, warp): the tag plane is cleared once per 126 calls instead of per call.
+        // 20 bits of round; a frame that needs more rounds (more than a million seeds taken one at a time) goes on
+        // with one region per round, which uses no tags
+        const int kmax = round < SG_ROUND_LIM ? SG_K : 1;
 #ifdef LSD_STATS
         t0 = clock64();
 #endif
@@ -1155,7 +1194,7 @@ __global__ void __launch_bounds__(SG_K * 32, SG_K == 8 ? 4 : 1) k_lsd_grow_spec(
                 for (int q = 0; q < 4; q++) {
                     u32 m = __ballot_sync(~0u, fr4[q]);
                     while (m && !stop) {
-                        if (k == SG_K || ne == SG_ENT) { stop = true; break; }
+                        if (k == kmax || ne == SG_ENT) { stop = true; break; }
                         const int j = __ffs(m) - 1;
                         m &= m - 1;
                         const u32 pj = __shfl_sync(~0u, pidx4[q], j);
@@ -1203,7 +1242,7 @@ __global__ void __launch_bounds__(SG_K * 32, SG_K == 8 ? 4 : 1) k_lsd_grow_spec(
             // tags); the others see its pixels as used -- late at worst, which the commit catches
             int n = wid == 0 ? lsd_grow(an, cs, reg, s_ring[0], W, H, sx, sy, P.prec, &reg_angle, lane)
                              : lsd_grow_spec(an, own, cs, reg, reg_cap, s_ring[wid], s_hset[wid], W, H, sx, sy, P.prec,
-                                             &reg_angle, lane, round, wid, &relied, &overflow);
+                                             &reg_angle, lane, (epoch << 20) | round, wid, &relied, &overflow);
             int need_refine = 0;
             LsdRect rec;
             if (!overflow && (unsigned)n >= P.min_reg_size) {
@@ -1474,7 +1513,11 @@ extern "C" int le_lsd(le_ctx *ctx, const uint8_t *gray, int n, int h, int w, int
     if ((rc = le_ensure(ctx, &ctx->lsd3, sizeof(u32) * npx * n))) return rc;                   // order
     const int spec = LE_KNOB_SET("LE_LSD_SERIAL") ? 0 : 1;  // development knob: the one-warp-per-frame kernel
     if ((rc = le_ensure(ctx, &ctx->lsd4, sizeof(u32) * npx * n * (spec ? 2 : 1)))) return rc;  // region lists
-    if (spec && (rc = le_ensure(ctx, &ctx->lsd7, sizeof(u32) * npx * n))) return rc;          // speculative tags
+    if (spec) {                                                                                // speculative tags
+        const void *before = ctx->lsd7.p;
+        if ((rc = le_ensure(ctx, &ctx->lsd7, sizeof(u32) * npx * n))) return rc;
+        if (ctx->lsd7.p != before) ctx->lsd_epoch = 0;  // a new buffer comes zeroed
+    }
     if ((rc = le_ensure(ctx, &ctx->lsd6, sizeof(float2) * npx * n))) return rc;                // cos/sin of the angles
     if ((rc = le_ensure(ctx, &ctx->lsd5, (sizeof(u16) + sizeof(u32)) * (size_t)nchunk * n_bins * n + 16))) return rc;
     ctx->edge_list_for = nullptr;
@@ -1580,7 +1623,11 @@ extern "C" int le_lsd(le_ctx *ctx, const uint8_t *gray, int n, int h, int w, int
     LE_T1(ctx, LE_K_LSD_PREP, st);
     LE_T0(ctx, LE_K_LSD_GROW, st);
     if (spec) {
-        LE_CUDA(ctx, cudaMemsetAsync(ctx->lsd7.p, 0, sizeof(u32) * npx * n, st));
+        if (ctx->lsd_epoch >= 126) {  // the epoch field of the tags is exhausted: clear the plane, start over
+            LE_CUDA(ctx, cudaMemsetAsync(ctx->lsd7.p, 0, ctx->lsd7.bytes, st));
+            ctx->lsd_epoch = 0;
+        }
+        const u32 epoch = (u32)++ctx->lsd_epoch;
         // warps per frame: 16 while every frame can have an SM of its own, else 8 (four CTAs per SM, 64 registers):
         // a second wave of CTAs costs more than the narrower rounds
         int K = n <= ctx->sm_count ? 16 : 8;
@@ -1597,7 +1644,7 @@ extern "C" int le_lsd(le_ctx *ctx, const uint8_t *gray, int n, int h, int w, int
     k_lsd_grow_spec<KK, AA><<<n, KK * 32, sg_smem, st>>>(img, (u32 *)ctx->lsd2.p, (u32 *)ctx->lsd7.p,               \
                                                          (const float2 *)ctx->lsd6.p, (const u32 *)ctx->lsd3.p,      \
                                                          (u32 *)ctx->lsd4.p, cnt, P, segs, width, prec_out,          \
-                                                         refine >= 2 ? nfa_out : nullptr, counts)
+                                                         refine >= 2 ? nfa_out : nullptr, counts, epoch)
         if (K == 16 && refine >= 2) LE_GROW(16, true);
         else if (K == 16) LE_GROW(16, false);
         else if (refine >= 2) LE_GROW(8, true);

@@ -55,14 +55,17 @@ def bind_to_gpu_numa_node(device_index):
 
 
 class _ChunkedHost:
-    """Two streams, two engines, two sets of device buffers; subclasses say what a chunk needs and does."""
+    """``streams`` CUDA streams, each with its own engine context and device buffers, take the chunks in turn;
+    subclasses say what a chunk needs and does.  Two streams hide the copy behind the kernels of a bandwidth-bound
+    chain; the chains whose kernels are bound by dependent latency inside a frame (HoughLinesP, LSD) take more, so
+    that several chunks are in their kernels at once."""
 
-    def __init__(self, h, w, device=0, chunk=32):
+    def __init__(self, h, w, device=0, chunk=32, streams=2):
         self.device = torch.device("cuda", device)
         self.h, self.w, self.chunk = h, w, chunk
-        self.streams = [torch.cuda.Stream(self.device) for _ in range(2)]
-        self.engines = [Engine(device) for _ in range(2)]
-        self.bufs = [self._alloc(chunk) for _ in range(2)]
+        self.streams = [torch.cuda.Stream(self.device) for _ in range(streams)]
+        self.engines = [Engine(device) for _ in range(streams)]
+        self.bufs = [self._alloc(chunk) for _ in range(streams)]
         self.h2d_bytes = 0
         self.d2h_bytes = 0
 
@@ -83,7 +86,8 @@ class _ChunkedHost:
         for ci, c0 in enumerate(range(0, n, self.chunk)):
             c1 = min(n, c0 + self.chunk)
             k = c1 - c0
-            s, eng, b = self.streams[ci & 1], self.engines[ci & 1], self.bufs[ci & 1]
+            si = ci % len(self.streams)
+            s, eng, b = self.streams[si], self.engines[si], self.bufs[si]
             with torch.cuda.stream(s):
                 b["src"][:k].copy_(frames[c0:c1], non_blocking=True)
                 res = self._chunk(eng, b, k)
@@ -134,10 +138,10 @@ class ProbHost(_ChunkedHost):
     -> (segs [N,max,4] i32 in cv2's order, counts [N])."""
 
     def __init__(self, h, w, device=0, chunk=16, max_segs=1024, lo=5, hi=150, rho=1.0, theta=np.pi / 180,
-                 threshold=30, min_line_length=50, max_line_gap=10):
+                 threshold=30, min_line_length=50, max_line_gap=10, streams=4):
         self.max_segs = max_segs
         self.params = (lo, hi, rho, theta, threshold, min_line_length, max_line_gap)
-        super().__init__(h, w, device, chunk)
+        super().__init__(h, w, device, chunk, streams)
 
     def _alloc(self, chunk):
         return dict(src=self._mk(chunk, self.h, self.w, 3), edges=self._mk(chunk, self.h, self.w))
@@ -152,10 +156,10 @@ class ProbHost(_ChunkedHost):
 class LsdHost(_ChunkedHost):
     """``lsd`` (opencv.py:204-209) for a batch: BGR -> gray -> LSD -> (segs [N,max,4] f32, counts [N])."""
 
-    def __init__(self, h, w, device=0, chunk=64, max_segs=2048, **lsd_params):
+    def __init__(self, h, w, device=0, chunk=64, max_segs=2048, streams=3, **lsd_params):
         self.max_segs = max_segs
         self.lsd_params = lsd_params
-        super().__init__(h, w, device, chunk)
+        super().__init__(h, w, device, chunk, streams)
 
     def _alloc(self, chunk):
         return dict(src=self._mk(chunk, self.h, self.w, 3))
@@ -171,11 +175,11 @@ class LinesVpHost(_ChunkedHost):
     segments longer than 10 px as polar lines -> fit -> (fit [N,3] f64 = (phi, theta, loss), pcounts [N])."""
 
     def __init__(self, h, w, device=0, chunk=32, max_segs=2048, iterations=1000, refinement_iterations=500,
-                 width=None, height=None):
+                 width=None, height=None, streams=4):
         self.max_segs = max_segs
         self.search = (iterations, refinement_iterations)
         self.size = (float(w if width is None else width), float(h if height is None else height))
-        super().__init__(h, w, device, chunk)
+        super().__init__(h, w, device, chunk, streams)
 
     def _alloc(self, chunk):
         return dict(src=self._mk(chunk, self.h, self.w, 3))
