@@ -34,7 +34,7 @@ PROTOTYPES = {
     "le_front_canny_u8": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _i, _i, _d, _d, _vp]),
     "le_hough_dims": (_i, [_i, _i, _d, _d, C.POINTER(_i), C.POINTER(_i)]),
     "le_hough_lines": (_i, [_vp, _vp, _i, _i, _i, _d, _d, _i, _vp, _vp, _vp, _vp, _i, _vp]),
-    "le_hough_lines_p": (_i, [_vp, _vp, _i, _i, _i, _d, _d, _i, _i, _i, _vp, _vp, _i, _vp]),
+    "le_hough_lines_p": (_i, [_vp, _vp, _i, _i, _i, _d, _d, _i, _i, _i, _vp, _vp, _i, _i, _vp]),
     "le_lsd_scaled_dims": (_i, [_i, _i, _d, C.POINTER(_i), C.POINTER(_i)]),
     "le_lsd": (_i, [_vp, _vp, _i, _i, _i, _i, _d, _d, _d, _d, _d, _d, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
     "le_segments_to_polar": (_i, [_vp, _vp, _i, _vp, _vp]),

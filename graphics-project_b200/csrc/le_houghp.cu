@@ -409,10 +409,14 @@ extern "C" void le_debug_ppht_trace(int32_t *dev_buf, int cap)
 
 extern "C" int le_hough_lines_p(le_ctx *ctx, const uint8_t *edges, int n, int h, int w, double rho, double theta,
                                 int threshold, int min_line_length, int max_line_gap, int32_t *segs,
-                                int32_t *counts, int max_segs, void *stream)
+                                int32_t *counts, int max_segs, int exact_order, void *stream)
 {
     LE_ON_DEVICE(ctx);
     if (!ctx) return LE_ERR_INVALID;
+    if (!exact_order)
+        return le_fail(ctx, LE_ERR_UNSUPPORTED, "HoughLinesP: only cv2's exact visiting order is implemented -- cv2 "
+                       "itself recalls under 40 %% of its segments at 1 px under another order, so an order-free "
+                       "mode cannot meet the 99 %% criterion (profiles/r2_ppht_order_sensitivity.txt)");
     LE_REQUIRE(ctx, edges && segs && counts, "null pointer");
     LE_REQUIRE(ctx, n > 0 && h > 0 && w > 0 && max_segs > 0, "n, h, w, max_segs must be positive");
     LE_REQUIRE(ctx, h < 65536 && w < 65536, "frame too large");

@@ -171,6 +171,18 @@ k_ppht_rounds(u8 *__restrict__ mask, const u32 *__restrict__ nz_g, u32 *__restri
     if (tid == 0) S.nlines = 0;
     int pos = 0;          // next pick
     int wbase = -PR_WIN;  // first pick of the staged window
+    // candidates per round adapt to the trigger rate: halved after two rounds in a row that triggered (the votes
+    // behind a trigger are issued and taken back), doubled after a round that did not.  Cube frames trigger in
+    // ~40 % of the rounds and stay at the cap; cave-style frames trigger in ~90 % and settle at 8
+    int cap_now = round_cap, streak = 0;
+#ifdef LE_PPHT_PROFILE  // phase cycle counters of frame 0 (variant build, scripts/ppht_profile.sh)
+    long long dbg[8] = {0, 0, 0, 0, 0, 0, 0, 0}, cnt_[6] = {0, 0, 0, 0, 0, 0}, t_a = clock64();
+#define PR_TICK(i) do { if (tid == 0) { long long t_ = clock64(); dbg[i] += t_ - t_a; t_a = t_; } } while (0)
+#define PR_CNT(i, v) do { if (tid == 0) cnt_[i] += (v); } while (0)
+#else
+#define PR_TICK(i) do { } while (0)
+#define PR_CNT(i, v) do { } while (0)
+#endif
     auto cell_of = [&](u32 pt) -> int {
         const float x = (float)(pt & 0xffff), y = (float)(pt >> 16);
         return __float2int_rn(__fadd_rn(__fmul_rn(x, tc), __fmul_rn(y, ts))) - rlo;
@@ -178,7 +190,7 @@ k_ppht_rounds(u8 *__restrict__ mask, const u32 *__restrict__ nz_g, u32 *__restri
 
     while (pos < count) {
         // ---- candidates of the round and their mask bytes (one round trip)
-        const int nb = min(round_cap, count - pos);
+        const int nb = min(cap_now, count - pos);
         if (pos + nb > wbase + PR_WIN || pos < wbase) {
             __syncthreads();  // readers of the previous window are done
             wbase = pos;
@@ -199,6 +211,8 @@ k_ppht_rounds(u8 *__restrict__ mask, const u32 *__restrict__ nz_g, u32 *__restri
             if (lane == 0) S.alive[wid] = b;
         }
         __syncthreads();
+        PR_TICK(0);
+        PR_CNT(0, 1);
         u32 al[NH], any_alive = 0;
 #pragma unroll
         for (int half = 0; half < NH; half++) {
@@ -252,11 +266,18 @@ k_ppht_rounds(u8 *__restrict__ mask, const u32 *__restrict__ nz_g, u32 *__restri
             if (lane == 0 && wmin < PR_B) atomicMin(&S.kstar, wmin);
         }
         __syncthreads();
+        PR_TICK(1);
+#ifdef LE_PPHT_PROFILE
+        for (int half = 0; half < NH; half++) PR_CNT(1, __popc(al[half]));
+#endif
         const int ks = S.kstar;
         if (ks == PR_B) {  // no trigger: every vote stands
             pos += nb;
+            cap_now = min(round_cap, cap_now * 2);
+            streak = 0;
             continue;
         }
+        if (++streak >= 2) cap_now = max(min(8, round_cap), cap_now >> 1);
         // ---- trigger at candidate ks: arg-max over the angles (highest value, then lowest angle)
         {
             const u32 key = (my_first == ks) ? (((u32)(my_val + 0x8000) << 8) | (u32)(255 - tid)) : 0u;
@@ -278,6 +299,8 @@ k_ppht_rounds(u8 *__restrict__ mask, const u32 *__restrict__ nz_g, u32 *__restri
             }
         }
         __syncthreads();
+        PR_TICK(2);
+        PR_CNT(2, 1);
         const u32 best = S.best;
         const int max_n = 255 - (int)(best & 255);
         const u32 ptk = cand[ks];
@@ -359,6 +382,7 @@ k_ppht_rounds(u8 *__restrict__ mask, const u32 *__restrict__ nz_g, u32 *__restri
             }
         }
         __syncthreads();
+        PR_TICK(3);
         const int e0x = S.end_xy[0][0], e0y = S.end_xy[0][1], e1x = S.end_xy[1][0], e1y = S.end_xy[1][1];
         const bool good = abs(e1x - e0x) >= line_length || abs(e1y - e0y) >= line_length;
         // second walk: clear the mask; un-vote (RED, no round trip) if the segment is accepted
@@ -375,23 +399,36 @@ k_ppht_rounds(u8 *__restrict__ mask, const u32 *__restrict__ nz_g, u32 *__restri
                 u32 bits = S.walk_on[k][wd];
                 if (wd == nwords - 1) bits &= (2u << (S.t_end[k] & 31)) - 1;  // chunks past the stop hold raw ballots
                 if (k == 1 && wd == 0) bits &= ~1u;  // the start pixel was handled by direction 0
+                // four pixels per trip: their cells are independent chains of ~10 dependent instructions each (one
+                // warp per scheduler has nothing else to issue), only the run-length combining is sequential
                 while (bits) {
-                    const int bpos = __ffs(bits) - 1;
-                    bits &= bits - 1;
-                    const int t = wd * 32 + bpos;
-                    const int x = x0 + t * dx, y = y0 + t * dy;
-                    const int j1 = xflag ? x : (x >> shift), i1 = xflag ? (y >> shift) : y;
-                    if (good && mine) {
-                        const int bb = __float2int_rn(__fadd_rn(__fmul_rn((float)j1, tc), __fmul_rn((float)i1, ts))) - rlo;
-                        if ((bb >> 1) != uw) {
-                            if (ud) atomicAdd(myrow + uw, 0u - ud);
-                            uw = bb >> 1;
-                            ud = 0;
-                        }
-                        ud += 1u << ((bb & 1) * 16);
+                    int tt[4], bbv[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        tt[u] = bits ? wd * 32 + __ffs(bits) - 1 : -1;
+                        bits &= bits - 1;
                     }
-                    if (q == tid) __stcg(mk + (size_t)i1 * w + j1, (u8)0);
-                    q = q + 1 == PR_THREADS ? 0 : q + 1;
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        const int t = max(tt[u], 0);
+                        const int x = x0 + t * dx, y = y0 + t * dy;
+                        const int j1 = xflag ? x : (x >> shift), i1 = xflag ? (y >> shift) : y;
+                        bbv[u] = __float2int_rn(__fadd_rn(__fmul_rn((float)j1, tc), __fmul_rn((float)i1, ts))) - rlo;
+                        if (tt[u] >= 0 && q == tid) __stcg(mk + (size_t)i1 * w + j1, (u8)0);
+                        if (tt[u] >= 0) q = q + 1 == PR_THREADS ? 0 : q + 1;
+                    }
+                    if (good && mine) {
+#pragma unroll
+                        for (int u = 0; u < 4; u++) {
+                            if (tt[u] < 0) continue;
+                            if ((bbv[u] >> 1) != uw) {
+                                if (ud) atomicAdd(myrow + uw, 0u - ud);
+                                uw = bbv[u] >> 1;
+                                ud = 0;
+                            }
+                            ud += 1u << ((bbv[u] & 1) * 16);
+                        }
+                    }
                 }
             }
         }
@@ -404,9 +441,18 @@ k_ppht_rounds(u8 *__restrict__ mask, const u32 *__restrict__ nz_g, u32 *__restri
             }
         }
         __syncthreads();  // mask stores are ordered before the next round's mask loads (same CTA, L2 accesses)
+        PR_TICK(4);
+        PR_CNT(3, good ? 1 : 0);
+        PR_CNT(4, S.t_end[0] + S.t_end[1]);
     }
     __syncthreads();
     if (tid == 0) counts[f] = S.nlines;
+#ifdef LE_PPHT_PROFILE
+    if (tid == 0 && f == 0)
+        printf("PPHTPROF count %d rounds %lld alive-voted %lld triggers %lld good %lld walk-steps %lld | cycles: cand+mask %lld "
+               "votes %lld trigger+rollback %lld walk %lld erase+unvote %lld\n", count, cnt_[0], cnt_[1], cnt_[2], cnt_[3],
+               cnt_[4], dbg[0], dbg[1], dbg[2], dbg[3], dbg[4]);
+#endif
 }
 
 int le_ppht_rounds_launch(le_ctx *ctx, int n, int h, int w, int numangle, int stride, int threshold, int min_len,
@@ -437,7 +483,11 @@ int le_ppht_rounds_launch(le_ctx *ctx, int n, int h, int w, int numangle, int st
     LE_T0(ctx, LE_K_PPHT, st);
     // candidates per round: measured on 128 x 4K cube frames 32 -> 8.1 ms, 64 -> 9.2, 128 -> 13.1 (votes behind a
     // trigger are issued and taken back: the SM's scattered-request rate pays for them twice)
-    const int round_cap = std::max(1, std::min(128, LE_KNOB_INT("LE_PPHT_B", 32)));  // development knob
+    // With more frames than SMs the CTAs of an SM share that rate and wasted votes cost more than round trips:
+    // 256 x 1080p 16 -> 6.0 ms (32: 6.7), 1024 x 1080p 8 -> 35.8 ms (16: 38.9, 32: 49.4)
+    const int round_dflt = n <= ctx->sm_count ? 32 : (n <= 2 * ctx->sm_count ? 16 : 8);
+    const int knob = LE_KNOB_INT("LE_PPHT_B", 0);  // development knob
+    const int round_cap = std::max(1, std::min(128, knob ? knob : round_dflt));
     const int nh = (round_cap + 31) / 32;
 #define LE_ROUNDS(NH)                                                                                             \
     k_ppht_rounds<NH><<<n, PR_THREADS, 0, st>>>((u8 *)ctx->ppht_mask.p, (const u32 *)ctx->ppht_nz.p,              \

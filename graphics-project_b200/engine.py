@@ -277,14 +277,17 @@ class Engine:
         return lines, votes, counts, accum
 
     # ------------------------------------------------------------------ a6
-    def hough_lines_p(self, edges, rho, theta, threshold, min_line_length=0, max_line_gap=0, max_segs=4096):
+    def hough_lines_p(self, edges, rho, theta, threshold, min_line_length=0, max_line_gap=0, max_segs=4096,
+                      exact_order=True):
+        """-> (segs [N,max_segs,4] i32 in cv2's emission order, counts [N] i32).  ``exact_order=False`` raises
+        LE_ERR_UNSUPPORTED: an order-free HoughLinesP cannot meet the 1 px / 99 % criterion (see the header)."""
         edges = self._img(edges, 1)
         n, h, w = edges.shape
         segs = torch.empty((n, max_segs, 4), dtype=torch.int32, device=self.device)
         counts = torch.empty((n,), dtype=torch.int32, device=self.device)
         self._ok(lib.le_hough_lines_p(self._ctx, _ptr(edges), n, h, w, float(rho), float(theta), int(threshold),
                                       int(min_line_length), int(max_line_gap), _ptr(segs), _ptr(counts), max_segs,
-                                      self._stream()))
+                                      int(bool(exact_order)), self._stream()))
         return segs, counts
 
     # ------------------------------------------------------------------ a7

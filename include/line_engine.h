@@ -97,7 +97,10 @@ int le_front_canny_u8(le_ctx *ctx, const uint8_t *src, int src_channels, int do_
  * accum (optional, may be NULL): int32 [n][numangle+2][numrho+2], fully written (no pre-zeroing needed).
  * lines: float32 [n][max_lines][2] (rho, theta), sorted by (votes desc, accumulator index asc);
  * votes (optional): int32 [n][max_lines];  counts: int32 [n].
- * le_hough_dims gives numangle / numrho for (h, w, rho, theta).                                  */
+ * le_hough_dims gives numangle / numrho for (h, w, rho, theta).
+ * counts[f] is the TRUE number of peaks; when it exceeds the peak list (max(4 * max_lines, 65536) entries) the
+ * frame's lines are an arbitrary subset and le_check reports LE_ERR_OVERFLOW.  (ceil(rho) + 1) * diagonal must
+ * stay below 65535 (16-bit stripe counters; cv2 counts in int32), else LE_ERR_UNSUPPORTED.                  */
 int le_hough_dims(int h, int w, double rho, double theta, int *numangle, int *numrho);
 int le_hough_lines(le_ctx *ctx, const uint8_t *edges, int n, int h, int w, double rho, double theta, int threshold,
                    int32_t *accum, float *lines, int32_t *votes, int32_t *counts, int max_lines, void *stream);
@@ -105,10 +108,15 @@ int le_hough_lines(le_ctx *ctx, const uint8_t *edges, int n, int h, int w, doubl
 /* ---- a6  replaces: cv.HoughLinesP(edges, rho, theta, threshold, minLineLength, maxLineGap)
  *                    opencv.py:35-37,217
  * Progressive probabilistic Hough, exact replay of cv::RNG(-1) visiting order.
- * segs: int32 [n][max_segs][4] (x1,y1,x2,y2) in cv2's emission order; counts: int32 [n].         */
+ * segs: int32 [n][max_segs][4] (x1,y1,x2,y2) in cv2's emission order; counts: int32 [n].
+ * exact_order: must be non-zero.  SURVEY 8(b) reserved 0 for an order-free mode graded by "every cv2 segment
+ * matched within 1 px, recall >= 99 %"; cv2's own algorithm under another RNG seed recalls 22-37 % of its
+ * segments at 1 px (profiles/r2_ppht_order_sensitivity.txt, tests/test_ppht_order.py), so no order-free variant
+ * can meet it: 0 returns LE_ERR_UNSUPPORTED instead of results that would fail the stated criterion.
+ * rho: (ceil(rho) + 1) * diagonal must stay below 32767 (16-bit accumulator cells), else LE_ERR_UNSUPPORTED.  */
 int le_hough_lines_p(le_ctx *ctx, const uint8_t *edges, int n, int h, int w, double rho, double theta,
                      int threshold, int min_line_length, int max_line_gap, int32_t *segs, int32_t *counts,
-                     int max_segs, void *stream);
+                     int max_segs, int exact_order, void *stream);
 
 /* ---- a7  replaces: cv.createLineSegmentDetector(refine, scale, sigma_scale, quant, ang_th, log_eps,
  *                    density_th, n_bins).detect(gray)          opencv.py:206-207 (refine 0), :142-145 (refine 2)

@@ -334,12 +334,17 @@ static int g_pp_trace_cap = 0, g_pp_trace_n = 0;
 void or_ppht_trace(int *buf, int cap) { g_pp_trace = buf; g_pp_trace_cap = cap; g_pp_trace_n = 0; }
 int or_ppht_trace_count(void) { return g_pp_trace_n; }
 
+/* cv2 seeds cv::RNG((uint64)-1) on every call; another seed gives another visiting order -- used only to measure
+ * how far the result depends on that order (tests/test_ppht_order.py, scripts/ppht_order_sensitivity.py). */
+static uint64_t g_pp_seed = (uint64_t)-1;
+void or_ppht_seed(uint64_t seed) { g_pp_seed = seed; }
+
 int or_hough_lines_p(const u8 *edges, int h, int w, float rho, float theta, int threshold,
                      int line_length, int line_gap, int *segs, int max_segs)
 {
     const int width = w, height = h;
     float irho = 1 / rho;
-    uint64_t rng = (uint64_t)-1;
+    uint64_t rng = g_pp_seed;
     int numangle = hough_numangle(0.0, M_PI, theta);
     int numrho = (int)lrint(((width + height) * 2 + 1) / rho);
     int *accum = (int *)calloc((size_t)numangle * numrho, sizeof(int));

@@ -137,8 +137,15 @@ def hough_lines(edges, rho, theta, threshold, max_lines=1 << 20, return_accum=Fa
     return res + (accum,) if return_accum else res
 
 
-def hough_lines_p(edges, rho, theta, threshold, min_len, max_gap, max_segs=1 << 18):
+def hough_lines_p(edges, rho, theta, threshold, min_len, max_gap, max_segs=1 << 18, seed=None):
+    """``seed`` replaces cv2's fixed cv::RNG(-1) state for ONE call (order-sensitivity measurements only)."""
     edges = _u8(edges)
+    if seed is not None:
+        lib().or_ppht_seed(C.c_uint64(seed))
+        try:
+            return hough_lines_p(edges, rho, theta, threshold, min_len, max_gap, max_segs)
+        finally:
+            lib().or_ppht_seed(C.c_uint64((1 << 64) - 1))
     h, w = edges.shape
     segs = np.empty((max_segs, 4), np.int32)
     n = lib().or_hough_lines_p(_p(edges), C.c_int(h), C.c_int(w), C.c_float(rho), C.c_float(theta),
