@@ -517,7 +517,7 @@ def run_engine(args, wl, rank, world, local_rank):
     B = args.batch or wl.batch
 
     # ---- synthetic input: frames are generated on the host once and uploaded before timing
-    _, uniq = make_frames(synth, wl, min(wl.unique, B), rank)
+    _, uniq = make_frames(synth, wl, min(wl.unique, B), rank if args.seed_rank < 0 else args.seed_rank)
     host_frames = torch.empty((B, wl.h, wl.w, 3), dtype=torch.uint8, pin_memory=True)
     for i in range(B):
         host_frames[i] = torch.from_numpy(uniq[i % len(uniq)])
@@ -698,6 +698,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--no-numa", action="store_true", help="do not bind the process to the GPU's NUMA node")
+    ap.add_argument("--seed-rank", type=int, default=-1, help="generate the frames rank R of a multi-GPU run would get")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -31,6 +31,7 @@ PROTOTYPES = {
     "le_gauss5_u8": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     "le_minmax_normalize_u8": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     "le_canny_u8": (_i, [_vp, _vp, _vp, _i, _i, _i, _d, _d, _vp]),
+    "le_canny_u8c3": (_i, [_vp, _vp, _vp, _i, _i, _i, _d, _d, _vp]),
     "le_front_canny_u8": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _i, _i, _d, _d, _vp]),
     "le_hough_dims": (_i, [_i, _i, _d, _d, C.POINTER(_i), C.POINTER(_i)]),
     "le_hough_lines": (_i, [_vp, _vp, _i, _i, _i, _d, _d, _i, _vp, _vp, _vp, _vp, _i, _vp]),

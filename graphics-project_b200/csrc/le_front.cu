@@ -415,6 +415,8 @@ extern "C" int le_minmax_normalize_u8(le_ctx *ctx, const uint8_t *src, uint8_t *
     return LE_OK;
 }
 
+static int launch_hysteresis(le_ctx *ctx, u8 *edges, int n, int h, int w, cudaStream_t st);
+
 int le_front_launch(le_ctx *ctx, const u8 *src, int ch, int do_blur, int do_norm, u8 *edges, int n, int h, int w,
                     int lo, int hi, cudaStream_t st)
 {
@@ -468,6 +470,70 @@ int le_front_launch(le_ctx *ctx, const u8 *src, int ch, int do_blur, int do_norm
     return LE_OK;
 }
 
+// ---- cv2.Canny on a 3-channel image (SURVEY Appendix B convention; no call site of the reference uses it, so
+// this is a plain one-thread-per-pixel kernel, not a tuned one).  Sobel per channel, the channel with the largest
+// |dx| + |dy| wins (the first on ties); NMS on that (dx, dy, magnitude); strong / weak lists as the fused front
+// kernel leaves them, so the usual hysteresis kernel finishes the job.
+static __device__ __forceinline__ int sobel_c3(const u8 *__restrict__ im, int h, int w, int x, int y, int *gx_out,
+                                               int *gy_out)
+{
+    if (x < 0 || x >= w || y < 0 || y >= h) return 0;  // cv2 pads the magnitude plane with zeros
+    const int xm = max(x - 1, 0), xp = min(x + 1, w - 1), ym = max(y - 1, 0), yp = min(y + 1, h - 1);
+    int best = -1;
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+#define P3(yy, xx) ((int)im[((size_t)(yy) * w + (xx)) * 3 + c])
+        const int gx = (P3(ym, xp) + 2 * P3(y, xp) + P3(yp, xp)) - (P3(ym, xm) + 2 * P3(y, xm) + P3(yp, xm));
+        const int gy = (P3(yp, xm) + 2 * P3(yp, x) + P3(yp, xp)) - (P3(ym, xm) + 2 * P3(ym, x) + P3(ym, xp));
+#undef P3
+        const int m = abs(gx) + abs(gy);
+        if (m > best) {
+            best = m;
+            *gx_out = gx;
+            *gy_out = gy;
+        }
+    }
+    return best;
+}
+
+__global__ void __launch_bounds__(256) k_canny_c3(const u8 *__restrict__ src, u8 *__restrict__ map,
+                                                  u32 *__restrict__ queue, int *__restrict__ counters, int h, int w,
+                                                  int lo, int hi)
+{
+    const int f = blockIdx.z;
+    const size_t npx = (size_t)h * w;
+    const u8 *im = src + (size_t)f * npx * 3;
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x >= w || y >= h) return;
+    int gx = 0, gy = 0, t0, t1;
+    const int mv = sobel_c3(im, h, w, x, y, &gx, &gy);
+    u8 out = 0;
+    if (mv > lo) {
+        const int ax = abs(gx), ay = abs(gy) << 15, tg22x = ax * 13573;
+        bool keep;
+        if (ay < tg22x) keep = mv > sobel_c3(im, h, w, x - 1, y, &t0, &t1) && mv >= sobel_c3(im, h, w, x + 1, y, &t0, &t1);
+        else if (ay > tg22x + (ax << 16))
+            keep = mv > sobel_c3(im, h, w, x, y - 1, &t0, &t1) && mv >= sobel_c3(im, h, w, x, y + 1, &t0, &t1);
+        else {
+            const int s = ((gx ^ gy) < 0) ? -1 : 1;
+            keep = mv > sobel_c3(im, h, w, x - s, y - 1, &t0, &t1) && mv > sobel_c3(im, h, w, x + s, y + 1, &t0, &t1);
+        }
+        if (keep) {
+            int *cnt = counters + f * LE_C_STRIDE;
+            u32 *q = queue + (size_t)f * npx;
+            const u32 idx = (u32)((size_t)y * w + x);
+            if (mv > hi) {
+                out = 255;
+                q[atomicAdd(&cnt[LE_C_QTAIL], 1)] = idx;
+            } else {
+                out = 1;
+                q[npx - 1 - (size_t)atomicAdd(&cnt[LE_C_WEAK], 1)] = idx;
+            }
+        }
+    }
+    map[(size_t)f * npx + (size_t)y * w + x] = out;
+}
+
 static int canny_thresholds(le_ctx *ctx, double lo, double hi, int *ilo, int *ihi)
 {
     LE_REQUIRE(ctx, lo == lo && hi == hi, "NaN threshold");
@@ -482,6 +548,46 @@ extern "C" int le_canny_u8(le_ctx *ctx, const uint8_t *src, uint8_t *edges, int 
 {
     LE_ON_DEVICE(ctx);
     return le_front_canny_u8(ctx, src, 1, 0, 0, edges, n, h, w, lo, hi, stream);
+}
+
+static int launch_hysteresis(le_ctx *ctx, u8 *edges, int n, int h, int w, cudaStream_t st)
+{
+    LE_T0(ctx, LE_K_HYST, st);
+    static le_dev_once hyst_attr;
+    if (hyst_attr.needs(ctx->device, 65536)) {
+        LE_CUDA(ctx, cudaFuncSetAttribute(k_hysteresis, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+        hyst_attr.done(ctx->device, 65536);
+    }
+    k_hysteresis<<<n, 1024, 65536, st>>>(edges, (u32 *)ctx->queue.p, (int *)ctx->counters.p, h, w);
+    LE_T1(ctx, LE_K_HYST, st);
+    LE_LAUNCH_CHECK(ctx);
+    ctx->edge_list_for = edges;
+    ctx->edge_list_n = n;
+    ctx->edge_list_h = h;
+    ctx->edge_list_w = w;
+    return LE_OK;
+}
+
+extern "C" int le_canny_u8c3(le_ctx *ctx, const uint8_t *src, uint8_t *edges, int n, int h, int w, double lo,
+                             double hi, void *stream)
+{
+    LE_ON_DEVICE(ctx);
+    int rc = check_img(ctx, src, edges, n, h, w);
+    if (rc) return rc;
+    LE_REQUIRE(ctx, src != edges, "in-place Canny is not supported");
+    int ilo, ihi;
+    if ((rc = canny_thresholds(ctx, lo, hi, &ilo, &ihi))) return rc;
+    if ((rc = front_scratch(ctx, n, h, w))) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    ctx->edge_list_for = nullptr;
+    k_zero_counters<<<((n + 1) * LE_C_STRIDE + 255) / 256, 256, 0, st>>>((int *)ctx->counters.p, n);
+    LE_LAUNCH_CHECK(ctx);
+    LE_T0(ctx, LE_K_FRONT, st);
+    k_canny_c3<<<dim3((w + 31) / 32, (h + 7) / 8, n), 256, 0, st>>>(src, edges, (u32 *)ctx->queue.p,
+                                                                    (int *)ctx->counters.p, h, w, ilo, ihi);
+    LE_T1(ctx, LE_K_FRONT, st);
+    LE_LAUNCH_CHECK(ctx);
+    return launch_hysteresis(ctx, edges, n, h, w, st);
 }
 
 extern "C" int le_front_canny_u8(le_ctx *ctx, const uint8_t *src, int src_channels, int do_blur, int do_normalize,

@@ -130,6 +130,77 @@ static __device__ void sort_frame(const u64 *pk, int total, int peak_cap, int nu
     const int n = min(total, peak_cap);
     if (threadIdx.x == 0) counts[f] = total;
     const int rowlen = numrho + 2;
+    auto emit = [&](u64 key, int rank) {
+        u32 idx = 0xffffffffu - (u32)(key & 0xffffffffu);
+        int v = (int)(key >> 32);
+        int nn = (int)(idx / (u32)rowlen) - 1;
+        int r = (int)idx - (nn + 1) * rowlen - 1;
+        float lr = __fmul_rn(__fsub_rn((float)r, __fmul_rn((float)(numrho - 1), 0.5f)), rho);
+        float lt = __fadd_rn(0.f, __fmul_rn((float)nn, theta));
+        float *o = lines + ((size_t)f * max_lines + rank) * 2;
+        o[0] = lr;
+        o[1] = lt;
+        if (votes) votes[(size_t)f * max_lines + rank] = v;
+    };
+    // Many peaks (textured frames: thousands per frame, the rank sort below is quadratic): only ranks below
+    // max_lines are emitted, and every key that can have such a rank has at least T votes, T = the largest vote
+    // count reached by max_lines keys or more.  A shared histogram of the vote counts finds T, the keys at or above
+    // it are compacted into the shared tile and ranked among themselves (all other keys are smaller).
+    constexpr int SF_BINS = 4096, SF_SMALL = 2048;
+    __shared__ int s_thr, s_m;
+    if (n > SF_SMALL && n > max_lines && tile_cap >= SF_BINS / 2) {
+        int *hist = (int *)tile;  // SF_BINS ints = SF_BINS / 2 tile entries
+        __syncthreads();
+        for (int i = threadIdx.x; i < SF_BINS; i += blockDim.x) hist[i] = 0;
+        __syncthreads();
+        for (int i = threadIdx.x; i < n; i += blockDim.x) atomicAdd(&hist[min((int)(__ldcg(pk + i) >> 32), SF_BINS - 1)], 1);
+        __syncthreads();
+        if (threadIdx.x < 32) {  // lane l owns bins [128 l, 128 l + 128): suffix sums over the lanes, then its own bins
+            const int lane = threadIdx.x;
+            int mine = 0;
+            for (int b = 0; b < SF_BINS / 32; b++) mine += hist[lane * (SF_BINS / 32) + b];
+            int above = 0;  // keys in the bins of higher lanes
+            for (int l = 31; l >= 0; l--) {  // (every lane takes part in every shuffle)
+                const int vl = __shfl_sync(~0u, mine, l);
+                if (l > lane) above += vl;
+            }
+            const bool here = above < max_lines && above + mine >= max_lines;
+            const u32 bal = __ballot_sync(~0u, here);
+            if (bal == 0 && lane == 0) s_thr = 0;  // fewer than max_lines keys in total: cannot happen here (n > max_lines)
+            if (here) {
+                int acc = above, T = lane * (SF_BINS / 32);
+                for (int b = SF_BINS / 32 - 1; b >= 0; b--) {
+                    acc += hist[lane * (SF_BINS / 32) + b];
+                    if (acc >= max_lines) { T = lane * (SF_BINS / 32) + b; break; }
+                }
+                s_thr = T;
+            }
+            if (lane == 0) s_m = 0;
+        }
+        __syncthreads();
+        const int T = s_thr;
+        if (T < SF_BINS - 1) {  // (the last bin holds every larger count: fall through to the full sort)
+            for (int i = threadIdx.x; i < n; i += blockDim.x) {
+                const u64 key = __ldcg(pk + i);
+                if ((int)(key >> 32) >= T) {
+                    const int pos = atomicAdd(&s_m, 1);
+                    if (pos < tile_cap) tile[pos] = key;
+                }
+            }
+            __syncthreads();
+            const int m = s_m;
+            if (m <= tile_cap) {
+                for (int i = threadIdx.x; i < m; i += blockDim.x) {
+                    const u64 key = tile[i];
+                    int rank = 0;
+                    for (int j = 0; j < m; j++) rank += tile[j] > key;
+                    if (rank < max_lines) emit(key, rank);
+                }
+                return;
+            }
+        }
+        __syncthreads();
+    }
     for (int i0 = 0; i0 < n; i0 += blockDim.x) {
         int i = i0 + threadIdx.x;
         u64 key = i < n ? __ldcg(pk + i) : 0;
@@ -142,18 +213,7 @@ static __device__ void sort_frame(const u64 *pk, int total, int peak_cap, int nu
             if (i < n)
                 for (int j = 0; j < tn; j++) rank += tile[j] > key;
         }
-        if (i < n && rank < max_lines) {
-            u32 idx = 0xffffffffu - (u32)(key & 0xffffffffu);
-            int v = (int)(key >> 32);
-            int nn = (int)(idx / (u32)rowlen) - 1;
-            int r = (int)idx - (nn + 1) * rowlen - 1;
-            float lr = __fmul_rn(__fsub_rn((float)r, __fmul_rn((float)(numrho - 1), 0.5f)), rho);
-            float lt = __fadd_rn(0.f, __fmul_rn((float)nn, theta));
-            float *o = lines + ((size_t)f * max_lines + rank) * 2;
-            o[0] = lr;
-            o[1] = lt;
-            if (votes) votes[(size_t)f * max_lines + rank] = v;
-        }
+        if (i < n && rank < max_lines) emit(key, rank);
     }
 }
 

@@ -210,18 +210,37 @@ __global__ void __launch_bounds__(256) k_blur_resize_w(const u8 *__restrict__ sr
         bl[ty][oc] = out;
     }
     __syncthreads();
+    // resize: the tile's column table (source column relative to the tile, its right neighbour, Q8 weight) is staged
+    // once; a thread produces FOUR neighbouring destination pixels and stores one word (dtw and dx0 are multiples
+    // of four: the host picks dtw that way) -- the per-pixel index arithmetic, table loads and byte stores of the
+    // one-pixel-per-thread loop were 47 % of the kernel's instructions (profiles/r2_ncu_digests.txt)
     const u8 *b8 = (const u8 *)bl;
-    for (int yy = threadIdx.x >> 5; yy < th; yy += 8) {
+    __shared__ u32 s_xt[SV_TW];
+    for (int xx = threadIdx.x; xx < tw; xx += 256) {
+        const int2 xt = xtab[dx0 + xx];
+        s_xt[xx] = (u32)(xt.x - x0) | ((u32)(min(xt.x + 1, w - 1) - x0) << 8) | ((u32)xt.y << 16);
+    }
+    __syncthreads();
+    const int ngrp = (tw + 3) >> 2;
+    for (int i = threadIdx.x; i < th * ngrp; i += 256) {
+        const int yy = i / ngrp, xg = (i - yy * ngrp) * 4;
         const int2 yt = ytab[dy0 + yy];
         const int r0 = (yt.x - y0) * SV_TW, r1 = (min(yt.x + 1, h - 1) - y0) * SV_TW;
-        for (int xx = threadIdx.x & 31; xx < tw; xx += 32) {
-            const int2 xt = xtab[dx0 + xx];
-            const int c0 = xt.x - x0, c1 = min(xt.x + 1, w - 1) - x0;
-            const u32 a = (u32)(256 - xt.y) * b8[r0 + c0] + (u32)xt.y * b8[r0 + c1];
-            const u32 b = (u32)(256 - xt.y) * b8[r1 + c0] + (u32)xt.y * b8[r1 + c1];
-            const u32 v = (u32)(256 - yt.y) * a + (u32)yt.y * b;
-            d[(size_t)(dy0 + yy) * dw + dx0 + xx] = (u8)((v + 32768u) >> 16);
+        const u32 wy1 = (u32)yt.y, wy0 = 256u - wy1;
+        u32 out = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const u32 e = s_xt[min(xg + k, tw - 1)];
+            const int c0 = (int)(e & 0xff), c1 = (int)((e >> 8) & 0xff);
+            const u32 wx1 = e >> 16, wx0 = 256u - wx1;
+            const u32 a = wx0 * b8[r0 + c0] + wx1 * b8[r0 + c1];
+            const u32 b = wx0 * b8[r1 + c0] + wx1 * b8[r1 + c1];
+            out |= ((wy0 * a + wy1 * b + 32768u) >> 16) << (8 * k);
         }
+        u8 *o = d + (size_t)(dy0 + yy) * dw + dx0 + xg;
+        if (xg + 4 <= tw && ((dw | dx0) & 3) == 0) *(u32 *)o = out;
+        else
+            for (int k = 0; k < 4 && xg + k < tw; k++) o[k] = (u8)(out >> (8 * k));
     }
 }
 
@@ -350,11 +369,30 @@ __global__ void __launch_bounds__(256) k_lsd_hist(const u8 *__restrict__ img, co
     __syncthreads();
     const double coef = lsd_bin_coef(counters, f, n_bins);
     size_t b0 = (size_t)c * LS_CHUNK, b1 = min(npx, b0 + LS_CHUNK);
-    for (size_t i = b0 + threadIdx.x; i < b1; i += 256) {
-        if (an[i] != LSD_NOTDEF) {
-            int y = (int)(i / W), x = (int)(i - (size_t)y * W), gx, gy;
-            atomicAdd(&sh[lsd_bin(grad_s(im, W, x, y, &gx, &gy), coef, n_bins)], 1u);
+    auto vote = [&](size_t i) {
+        int y = (int)(i / W), x = (int)(i - (size_t)y * W), gx, gy;
+        atomicAdd(&sh[lsd_bin(grad_s(im, W, x, y, &gx, &gy), coef, n_bins)], 1u);
+    };
+    if ((npx & 3) == 0 && (((size_t)an) & 15) == 0) {
+        // 16 bytes of angle words per thread and load, two loads in flight: the kernel was bound by the latency of
+        // one 4-byte load per thread and trip (39 long-scoreboard stall cycles per issue, 25 % of the DRAM rate)
+        const uint4 *a4 = (const uint4 *)an;
+        for (size_t v = b0 / 4 + threadIdx.x; v < b1 / 4; v += 512) {
+            const uint4 q0 = __ldg(a4 + v);
+            const bool two = v + 256 < b1 / 4;
+            const uint4 q1 = two ? __ldg(a4 + v + 256) : make_uint4(LSD_NOTDEF, LSD_NOTDEF, LSD_NOTDEF, LSD_NOTDEF);
+            if (q0.x != LSD_NOTDEF) vote(4 * v);
+            if (q0.y != LSD_NOTDEF) vote(4 * v + 1);
+            if (q0.z != LSD_NOTDEF) vote(4 * v + 2);
+            if (q0.w != LSD_NOTDEF) vote(4 * v + 3);
+            if (q1.x != LSD_NOTDEF) vote(4 * (v + 256));
+            if (q1.y != LSD_NOTDEF) vote(4 * (v + 256) + 1);
+            if (q1.z != LSD_NOTDEF) vote(4 * (v + 256) + 2);
+            if (q1.w != LSD_NOTDEF) vote(4 * (v + 256) + 3);
         }
+    } else {
+        for (size_t i = b0 + threadIdx.x; i < b1; i += 256)
+            if (an[i] != LSD_NOTDEF) vote(i);
     }
     __syncthreads();
     u16 *o = chist + ((size_t)f * nchunk + c) * n_bins;
@@ -413,12 +451,19 @@ __global__ void __launch_bounds__(32) k_lsd_scatter(const u8 *__restrict__ img, 
     size_t b0 = (size_t)c * LS_CHUNK, b1 = min(npx, b0 + LS_CHUNK);
     // 128 pixels per trip: the four angle words of a lane are fetched together (one memory round per trip
     // instead of four), then ranked 32 at a time in row-major order
+    u32 nx[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const size_t i = b0 + 32 * q + lane;
+        nx[q] = i < b1 ? __ldg(an + i) : LSD_NOTDEF;
+    }
     for (size_t j0 = b0; j0 < b1; j0 += 128) {
         u32 av[4];
 #pragma unroll
         for (int q = 0; q < 4; q++) {
-            const size_t i = j0 + 32 * q + lane;
-            av[q] = i < b1 ? __ldg(an + i) : LSD_NOTDEF;
+            av[q] = nx[q];
+            const size_t i = j0 + 128 + 32 * q + lane;  // the next trip's words are in flight while this one is ranked
+            nx[q] = i < b1 ? __ldg(an + i) : LSD_NOTDEF;
         }
 #pragma unroll
         for (int q = 0; q < 4; q++) {
@@ -1158,7 +1203,12 @@ __global__ void __launch_bounds__(SG_K * 32, SG_K == 8 ? 4 : 1) k_lsd_grow_spec(
     __shared__ u32 s_ent_seed[SG_ENT], s_ent_xy[SG_ENT];
     __shared__ int s_ent_ord[SG_ENT], s_ent_kind[SG_ENT];
     __shared__ int s_pos, s_k, s_ne, s_nseg;
+    // pre-commit results: per slot (bit 0: a pixel is USED, bit 1: the seed is), the earlier regions of the round
+    // that share a pixel with it / hold its seed; per deferred seed the same two facts; and who marks below
+    __shared__ int s_pre[SG_K], s_act[SG_K], s_def_used[SG_ENT];
+    __shared__ u32 s_ovl[SG_K], s_sw[SG_K], s_def_sw[SG_ENT];
     if (threadIdx.x == 0) { s_pos = 0; s_nseg = 0; }
+    if (threadIdx.x < SG_K) s_act[threadIdx.x] = 0;
     __syncthreads();
 #ifdef LSD_STATS
     long long t_sel = 0, t_grow = 0, t_com = 0, t0 = 0;
@@ -1271,152 +1321,168 @@ __global__ void __launch_bounds__(SG_K * 32, SG_K == 8 ? 4 : 1) k_lsd_grow_spec(
 #ifdef LSD_STATS
         t_grow += clock64() - t0; t0 = clock64();
 #endif
-        // ---- ordered commit (warp 0)
+        // ---- pre-commit, every warp for its own region (round 1 did all of this on warp 0, region after region,
+        // three dependent L2 round trips each: 29 % of the kernel).  After the barrier above every region of the
+        // round is grown, region 0 has marked its pixels and every pixel set (hash) is complete, so a region can
+        // find out by itself (a) whether any of its pixels -- the seed first -- is USED already, and (b) which
+        // earlier regions of the round share a pixel with it or hold its seed.  What is still unknown is which of
+        // those regions will COMMIT; that is decided in list order below from these bit masks alone.
+        auto in_set = [&](int v, u32 e) -> bool {
+            for (u32 hx = sg_hash(e);; hx = (hx + 1) & (SG_HASH - 1)) {
+                const u32 t = ((volatile u32 *)s_hset[v])[hx];
+                if (t == e) return true;
+                if (t == 0xFFFFFFFFu) return false;
+            }
+        };
+        if (wid > 0 && wid < kc && !s_slot[wid].serial) {
+            const int n = s_slot[wid].n;
+            bool used_any = false, seed_used = false;
+            u32 ovl = 0, sw = 0;
+            for (int base = 0; base < n; base += 128) {
+                u32 pt[4], av[4];
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const int i = base + 32 * q + lane;
+                    pt[q] = i < n ? ((n - i <= LSD_RING) ? ((volatile u32 *)s_ring[wid])[i & (LSD_RING - 1)] : ld_cg(reg + i))
+                                  : 0xFFFFFFFFu;
+                }
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+                    av[q] = pt[q] != 0xFFFFFFFFu ? ld_cg((const u32 *)an + (size_t)(pt[q] >> 16) * W + (pt[q] & 0xffff)) : 0u;
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    if (pt[q] == 0xFFFFFFFFu) continue;
+                    const bool first = base + 32 * q + lane == 0;
+                    if (av[q] & LSD_USED) {
+                        used_any = true;
+                        seed_used = seed_used || first;
+                    }
+                    for (int v = 1; v < wid; v++) {
+                        if (s_slot[v].serial || !in_set(v, pt[q])) continue;
+                        ovl |= 1u << v;
+                        if (first) sw |= 1u << v;
+                    }
+                }
+            }
+            used_any = __any_sync(~0u, used_any);
+            seed_used = __any_sync(~0u, seed_used);
+            ovl = __reduce_or_sync(~0u, ovl);
+            sw = __reduce_or_sync(~0u, sw);
+            if (lane == 0) {
+                s_pre[wid] = (used_any ? 1 : 0) | (seed_used ? 2 : 0);
+                s_ovl[wid] = ovl;
+                s_sw[wid] = sw;
+            }
+        }
+        if (wid == 0) {  // the deferred seeds: USED already, or inside one of the round's regions
+            const int ne = s_ne;
+            for (int e = lane; e < ne; e += 32) {
+                if (s_ent_kind[e] >= 0) continue;
+                u32 m = 0;
+                for (int v = 1; v < kc; v++)
+                    if (!s_slot[v].serial && in_set(v, s_ent_xy[e])) m |= 1u << v;
+                s_def_sw[e] = m;
+                s_def_used[e] = (ld_cg((const u32 *)an + s_ent_seed[e]) & LSD_USED) ? 1 : 0;
+            }
+        }
+        __syncthreads();
+        // ---- ordered decisions (warp 0; no memory round trips except for a refinement)
         if (wid == 0) {
-            u32 bad = 0;
+            u32 bad = 0, committed = 0;
             int nseg = s_nseg;
             const int ne = s_ne;
             int e = 0;
-#ifdef LSD_STATS
-            int st_commit = 0, st_void = 0, st_why = 0;
-            long long c_def = 0, c_seed = 0, c_val = 0, c_mark = 0, c_out = 0, c0;
-#define CT(x) do { long long c1 = clock64(); x += c1 - c0; c0 = c1; } while (0)
-            c0 = clock64();
-#else
-#define CT(x)
-#endif
             for (; e < ne; e++) {
                 const int w = s_ent_kind[e];
                 if (w < 0) {  // deferred seed: swallowed by now (the usual case), or the round ends here
-                    if (ld_cg((const u32 *)an + s_ent_seed[e]) & LSD_USED) { CT(c_def); continue; }
-#ifdef LSD_STATS
-                    st_why = 1;
-#endif
+                    if (s_def_used[e] || (s_def_sw[e] & committed)) continue;
                     break;
                 }
                 const SgSlot *S = &s_slot[w];
-#ifdef LSD_STATS
-                if (S->serial && w > 0) { st_why = 2; break; }
-#else
                 if (S->serial && w > 0) break;
-#endif
-                if (w > 0 && (ld_cg((const u32 *)an + S->seed) & LSD_USED)) {  // swallowed by an earlier region of this round
-                    bad |= 1u << w;
-#ifdef LSD_STATS
-                    st_void++;
-#endif
-                    CT(c_seed);
-                    continue;
-                }
-                CT(c_seed);
-                int n = S->n;
-                const u32 *rg = w == 0 ? reg0 : reg0 + npx + (size_t)(w - 1) * cap_w;
                 if (w > 0) {
-#ifdef LSD_STATS
-                    if (bad == ~0u || (S->relied & bad)) { st_why = 3; break; }
-                    if (S->need_refine) { st_why = 4; break; }
-#else
-                    if (bad == ~0u || (S->relied & bad)) break;
+                    if ((s_pre[w] & 2) || (s_sw[w] & committed)) {  // swallowed by an earlier region of this round
+                        bad |= 1u << w;
+                        continue;
+                    }
+                    if (S->relied & bad) break;
                     if (S->need_refine) break;
-#endif
-                    // every pixel must still be free: all earlier regions of the round are committed by now.
-                    // 256 pixels per trip (eight per lane): the list entries, then their words, are fetched
-                    // together -- two memory rounds per trip instead of two per 32 pixels
-                    bool ok = true;
-                    u32 pt[8], av[8];
-                    for (int base = 0; base < n; base += 256) {
-#pragma unroll
-                        for (int q = 0; q < 8; q++) {
-                            const int i = base + 32 * q + lane;
-                            pt[q] = i < n ? ld_cg(rg + i) : 0xFFFFFFFFu;
-                        }
-#pragma unroll
-                        for (int q = 0; q < 8; q++)
-                            av[q] = pt[q] != 0xFFFFFFFFu ? ld_cg((const u32 *)an + (size_t)(pt[q] >> 16) * W + (pt[q] & 0xffff)) : 0u;
-#pragma unroll
-                        for (int q = 0; q < 8; q++) ok = ok && !(av[q] & LSD_USED);
-                    }
-#ifdef LSD_STATS
-                    if (!__all_sync(~0u, ok)) { st_why = 5; break; }
-                    st_commit++;
-                    CT(c_val);
-#else
-                    if (!__all_sync(~0u, ok)) break;
-#endif
-                    if (n <= 256) {  // still in registers
-#pragma unroll
-                        for (int q = 0; q < 8; q++)
-                            if (pt[q] != 0xFFFFFFFFu) an[(size_t)(pt[q] >> 16) * W + (pt[q] & 0xffff)] = av[q] | LSD_USED;
-                    } else {
-                        for (int base = 0; base < n; base += 256) {
-#pragma unroll
-                            for (int q = 0; q < 8; q++) {
-                                const int i = base + 32 * q + lane;
-                                pt[q] = i < n ? ld_cg(rg + i) : 0xFFFFFFFFu;
-                            }
-#pragma unroll
-                            for (int q = 0; q < 8; q++)
-                                av[q] = pt[q] != 0xFFFFFFFFu ? ld_cg((const u32 *)an + (size_t)(pt[q] >> 16) * W + (pt[q] & 0xffff)) : 0u;
-#pragma unroll
-                            for (int q = 0; q < 8; q++)
-                                if (pt[q] != 0xFFFFFFFFu) an[(size_t)(pt[q] >> 16) * W + (pt[q] & 0xffff)] = av[q] | LSD_USED;
-                        }
-                    }
+                    // every pixel must still be free: not USED when the round's growth ended, and in no region
+                    // that committed before this one
+                    if ((s_pre[w] & 1) || (s_ovl[w] & committed)) break;
+                    committed |= 1u << w;
+                    if (lane == 0) s_act[w] = 1;  // the owning warp marks the pixels below
                 }
-                __syncwarp();
-                CT(c_mark);
+                int n = S->n;
                 if ((unsigned)n < P.min_reg_size) continue;
                 LsdRect rec = S->rec;
                 double reg_angle = S->reg_angle;
-                if (S->need_refine) {  // only the first region of a round: the sequential refinement path
-                    bad = ~0u;  // its pixel set changes: nobody else of this round may commit
-                    if (!lsd_refine(im, an, cs, reg0, s_ring[0], &n, W, H, &reg_angle, P.prec, &rec, P.density_th, lane))
-                        continue;
+                bool refined = false;
+                if (S->need_refine) {  // only the first region of a round: the sequential refinement path.  Its
+                    // pixel set changes, so the masks above are stale: the round ends behind this region (what the
+                    // entries behind it are -- swallowed, void or free -- the next round's seed scan finds out)
+                    refined = true;
+                    if (!lsd_refine(im, an, cs, reg0, s_ring[0], &n, W, H, &reg_angle, P.prec, &rec, P.density_th, lane)) {
+                        e++;
+                        break;
+                    }
                     rec.prec = P.prec;
                     rec.p = P.p;
                 }
                 double log_nfa = S->log_nfa;
+                bool emit = true;
                 if (ADV) {
                     if (S->need_refine) log_nfa = lsd_rect_improve(an, W, H, rec, P.log_nt, P.log_eps, lane);
-                    if (log_nfa <= P.log_eps) continue;
+                    emit = log_nfa > P.log_eps;
                 }
-                rec.x1 += 0.5; rec.y1 += 0.5; rec.x2 += 0.5; rec.y2 += 0.5;
-                if (P.scale != 1) {
-                    rec.x1 /= P.scale; rec.y1 /= P.scale; rec.x2 /= P.scale; rec.y2 /= P.scale;
-                    rec.width /= P.scale;
+                if (emit) {
+                    rec.x1 += 0.5; rec.y1 += 0.5; rec.x2 += 0.5; rec.y2 += 0.5;
+                    if (P.scale != 1) {
+                        rec.x1 /= P.scale; rec.y1 /= P.scale; rec.x2 /= P.scale; rec.y2 /= P.scale;
+                        rec.width /= P.scale;
+                    }
+                    if (lane == 0 && nseg < P.max_segs) {
+                        float *o = segs + ((size_t)f * P.max_segs + nseg) * 4;
+                        o[0] = (float)rec.x1; o[1] = (float)rec.y1; o[2] = (float)rec.x2; o[3] = (float)rec.y2;
+                        if (widths) widths[(size_t)f * P.max_segs + nseg] = rec.width;
+                        if (precs) precs[(size_t)f * P.max_segs + nseg] = rec.p;
+                        if (nfas) nfas[(size_t)f * P.max_segs + nseg] = log_nfa;
+                    }
+                    nseg++;
                 }
-                if (lane == 0 && nseg < P.max_segs) {
-                    float *o = segs + ((size_t)f * P.max_segs + nseg) * 4;
-                    o[0] = (float)rec.x1; o[1] = (float)rec.y1; o[2] = (float)rec.x2; o[3] = (float)rec.y2;
-                    if (widths) widths[(size_t)f * P.max_segs + nseg] = rec.width;
-                    if (precs) precs[(size_t)f * P.max_segs + nseg] = rec.p;
-                    if (nfas) nfas[(size_t)f * P.max_segs + nseg] = log_nfa;
+                if (refined) {
+                    e++;
+                    break;
                 }
-                nseg++;
-                CT(c_out);
             }
-#ifdef LSD_STATS
-            if (lane == 0 && f == 0) {
-                atomicAdd((unsigned long long *)&g_lsd_cyc[0], (unsigned long long)c_def); atomicAdd((unsigned long long *)&g_lsd_cyc[1], (unsigned long long)c_seed);
-                atomicAdd((unsigned long long *)&g_lsd_cyc[2], (unsigned long long)c_val); atomicAdd((unsigned long long *)&g_lsd_cyc[3], (unsigned long long)c_mark);
-                atomicAdd((unsigned long long *)&g_lsd_cyc[4], (unsigned long long)c_out);
-            }
-#endif
             if (lane == 0) {
                 s_nseg = nseg;
                 s_pos = e < ne ? s_ent_ord[e] : s_ent_ord[ne - 1] + 1;
-#ifdef LSD_STATS
-                if (f == 0) {
-                    atomicAdd(&g_lsd_stats[0], 1); atomicAdd(&g_lsd_stats[1], kc); atomicAdd(&g_lsd_stats[2], ne);
-                    atomicAdd(&g_lsd_stats[3], st_commit); atomicAdd(&g_lsd_stats[4], st_void); atomicAdd(&g_lsd_stats[5 + st_why], 1);
-                }
-#endif
             }
         }
-#ifdef LSD_STATS
-        if (threadIdx.x == 0 && f == 0) atomicAdd((unsigned long long *)&g_lsd_cyc[5], (unsigned long long)(clock64() - t0));
-        if (threadIdx.x == 32 && f == 0) atomicAdd((unsigned long long *)&g_lsd_cyc[6], (unsigned long long)(clock64() - t0));
-#endif
+        __syncthreads();
+        // ---- the committed regions mark their pixels USED, each warp its own (plain stores of the angle word, like
+        // the sequential path: the frame's angle plane is read through L1 by this SM only)
+        if (wid > 0 && wid < kc && s_act[wid]) {
+            const int n = s_slot[wid].n;
+            for (int base = 0; base < n; base += 128) {
+                u32 pt[4], av[4];
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const int i = base + 32 * q + lane;
+                    pt[q] = i < n ? ((n - i <= LSD_RING) ? ((volatile u32 *)s_ring[wid])[i & (LSD_RING - 1)] : ld_cg(reg + i))
+                                  : 0xFFFFFFFFu;
+                }
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+                    av[q] = pt[q] != 0xFFFFFFFFu ? ld_cg((const u32 *)an + (size_t)(pt[q] >> 16) * W + (pt[q] & 0xffff)) : 0u;
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+                    if (pt[q] != 0xFFFFFFFFu) an[(size_t)(pt[q] >> 16) * W + (pt[q] & 0xffff)] = av[q] | LSD_USED;
+            }
+            __syncwarp();
+            if (lane == 0) s_act[wid] = 0;
+        }
         __syncthreads();
 #ifdef LSD_STATS
         t_com += clock64() - t0;
@@ -1547,7 +1613,7 @@ extern "C" int le_lsd(le_ctx *ctx, const uint8_t *gray, int n, int h, int w, int
                 }
                 return true;
             };
-            for (dtw = std::min(W, (int)((SV_TW - 5) * scale)); dtw >= 16 && !fits(xt, w, dtw, SV_TW, 3); dtw--) {}
+            for (dtw = std::min(W, (int)((SV_TW - 5) * scale)) & ~3; dtw >= 16 && !fits(xt, w, dtw, SV_TW, 3); dtw -= 4) {}
             for (dth = std::min(H, (int)((SV_TH - 2) * scale)); dth >= 4 && !fits(yt, h, dth, SV_TH, 0); dth--) {}
             if (dtw < 16 || dth < 4) dtw = dth = 0;
         }

@@ -108,6 +108,9 @@ def Canny(image, threshold1, threshold2, edges=None, apertureSize=3, L2gradient=
     """cv.Canny(img, lo, hi[, apertureSize=3]) -- opencv.py:26,214; opencv_fit_color.py:78."""
     if apertureSize != 3 or L2gradient:
         raise _err("Canny: only apertureSize=3, L2gradient=False is on the hot path")
+    if isinstance(image, np.ndarray) and image.dtype == np.uint8 and image.ndim == 3 and image.shape[2] == 3:
+        eng, t = _dev(image)  # cv2 accepts a 3-channel image: per pixel the channel with the largest gradient
+        return eng.canny_c3(t[None], threshold1, threshold2)[0].cpu().numpy()
     _check_u8(image, 1, "Canny")
     eng, t = _dev(image)
     return eng.canny(t[None], threshold1, threshold2)[0].cpu().numpy()

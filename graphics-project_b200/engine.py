@@ -137,6 +137,18 @@ class Engine:
     def canny(self, gray, lo, hi, out=None):
         return self.front_canny(gray, lo, hi, blur=False, normalize=False, out=out)
 
+    def canny_c3(self, src, lo, hi, out=None):
+        """cv.Canny on 3-channel images [N,H,W,3] (per pixel the channel with the largest |dx|+|dy|; a cv2
+        convention, not the BGR->gray chain of ``front_canny``)."""
+        src = self._img(src, 3)
+        n, h, w = src.shape[:3]
+        if out is None:
+            out = torch.empty((n, h, w), dtype=torch.uint8, device=self.device)
+        self._out(out, (n, h, w), torch.uint8, "canny_c3 out")
+        self._ok(lib.le_canny_u8c3(self._ctx, _ptr(src), _ptr(out), n, h, w, float(lo), float(hi), self._stream()))
+        self._last_edges_shape = (n, h, w)
+        return out
+
     def front_canny(self, src, lo, hi, blur=False, normalize=False, out=None, channels=None):
         """[BGR->gray] -> [blur5] -> [normalize] -> Canny.  ``src`` is [N,H,W,3] BGR or [N,H,W] gray (or one gray
         frame [H,W]).  A 3-D tensor whose last dimension is 3 is ambiguous (one BGR frame, or H gray frames three

@@ -81,6 +81,12 @@ int le_minmax_normalize_u8(le_ctx *ctx, const uint8_t *src, uint8_t *dst, int n,
 int le_canny_u8(le_ctx *ctx, const uint8_t *src, uint8_t *edges, int n, int h, int w, double lo, double hi,
                 void *stream);
 
+/* cv.Canny on a 3-CHANNEL image (a cv2 convention; no call site of the reference passes one):
+ * Sobel per channel, every pixel keeps the channel with the largest |dx| + |dy| (the first on ties), then NMS
+ * and hysteresis as above.  src: uint8 [n][h][w][3].  Leaves the per-frame edge lists like le_front_canny_u8. */
+int le_canny_u8c3(le_ctx *ctx, const uint8_t *src, uint8_t *edges, int n, int h, int w, double lo, double hi,
+                  void *stream);
+
 /* Fused front end: [BGR->gray] -> [blur5] -> [minmax normalize] -> Canny, one pass over the input.
  *   src_channels: 3 (BGR) or 1 (gray);  do_blur, do_normalize: 0/1.
  * Covers prob() (3,0,0,5,150; opencv.py:213-214), get_camera_angles 'hough' (3,1,0,5,10;

@@ -172,7 +172,10 @@ void or_f32_normalize_minmax(const float *src, float *dst_f32, u8 *dst_u8, long 
 
 /* ---------------------------------------------------------------- a4: Canny
  * nms_out (optional): 0 = none, 1 = weak candidate, 2 = strong candidate.    */
-void or_canny(const u8 *src, u8 *dst, int h, int w, double lo_d, double hi_d, u8 *nms_out)
+/* cn = 1: a gray image.  cn = 3: cv2.Canny on an interleaved 3-channel image ("Canny accepts
+ * 3-channel input") -- the Sobel derivatives are taken per channel and every pixel keeps the channel with the
+ * largest |dx| + |dy| (the first one on ties); NMS and hysteresis then run on that single (dx, dy, magnitude). */
+static void canny_cn(const u8 *src, int cn, u8 *dst, int h, int w, double lo_d, double hi_d, u8 *nms_out)
 {
     if (lo_d > hi_d) { double t = lo_d; lo_d = hi_d; hi_d = t; }
     int lo = (int)floor(lo_d), hi = (int)floor(hi_d);
@@ -186,13 +189,18 @@ void or_canny(const u8 *src, u8 *dst, int h, int w, double lo_d, double hi_d, u8
         int ym = clampi(y - 1, 0, h - 1), yp = clampi(y + 1, 0, h - 1);
         for (int x = 0; x < w; x++) {
             int xm = clampi(x - 1, 0, w - 1), xp = clampi(x + 1, 0, w - 1);
-#define P(yy, xx) ((int)src[(size_t)(yy) * w + (xx)])
-            int gx = (P(ym, xp) + 2 * P(y, xp) + P(yp, xp)) - (P(ym, xm) + 2 * P(y, xm) + P(yp, xm));
-            int gy = (P(yp, xm) + 2 * P(yp, x) + P(yp, xp)) - (P(ym, xm) + 2 * P(ym, x) + P(ym, xp));
+            int bgx = 0, bgy = 0, bm = -1;
+            for (int c = 0; c < cn; c++) {
+#define P(yy, xx) ((int)src[((size_t)(yy) * w + (xx)) * cn + c])
+                int gx = (P(ym, xp) + 2 * P(y, xp) + P(yp, xp)) - (P(ym, xm) + 2 * P(y, xm) + P(yp, xm));
+                int gy = (P(yp, xm) + 2 * P(yp, x) + P(yp, xp)) - (P(ym, xm) + 2 * P(ym, x) + P(ym, xp));
 #undef P
-            dx[(size_t)y * w + x] = (short)gx;
-            dy[(size_t)y * w + x] = (short)gy;
-            mag[(size_t)(y + 1) * ms + x + 1] = abs(gx) + abs(gy);
+                int m = abs(gx) + abs(gy);
+                if (m > bm) { bm = m; bgx = gx; bgy = gy; }
+            }
+            dx[(size_t)y * w + x] = (short)bgx;
+            dy[(size_t)y * w + x] = (short)bgy;
+            mag[(size_t)(y + 1) * ms + x + 1] = bm;
         }
     }
     const int TG22 = 13573;
@@ -234,6 +242,15 @@ void or_canny(const u8 *src, u8 *dst, int h, int w, double lo_d, double hi_d, u8
     }
     for (size_t i = 0; i < n; i++) dst[i] = (map[i] == 2) ? 255 : 0;
     free(dx); free(dy); free(mag); free(map); free(stack);
+}
+
+void or_canny(const u8 *src, u8 *dst, int h, int w, double lo_d, double hi_d, u8 *nms_out)
+{
+    canny_cn(src, 1, dst, h, w, lo_d, hi_d, nms_out);
+}
+void or_canny_c3(const u8 *src, u8 *dst, int h, int w, double lo_d, double hi_d, u8 *nms_out)
+{
+    canny_cn(src, 3, dst, h, w, lo_d, hi_d, nms_out);
 }
 
 /* ------------------------------------------------------ a5: standard Hough */

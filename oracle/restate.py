@@ -101,12 +101,14 @@ def f32_do_canny(view, lo=30, hi=50):
 
 
 def canny(src, lo, hi, return_nms=False):
+    """Gray [H,W], or a 3-channel image [H,W,3] (cv2 keeps, per pixel, the channel with the largest |dx|+|dy|)."""
     src = _u8(src)
-    h, w = src.shape
-    out = np.empty_like(src)
-    nms = np.empty_like(src) if return_nms else None
-    lib().or_canny(_p(src), _p(out), C.c_int(h), C.c_int(w), C.c_double(lo), C.c_double(hi),
-                   _p(nms) if return_nms else None)
+    h, w = src.shape[:2]
+    out = np.empty((h, w), np.uint8)
+    nms = np.empty((h, w), np.uint8) if return_nms else None
+    fn = lib().or_canny_c3 if src.ndim == 3 else lib().or_canny
+    assert src.ndim == 2 or src.shape[2] == 3
+    fn(_p(src), _p(out), C.c_int(h), C.c_int(w), C.c_double(lo), C.c_double(hi), _p(nms) if return_nms else None)
     return (out, nms) if return_nms else out
 
 

@@ -175,3 +175,27 @@ def test_segments_starting_on_flat_rows(engine, batch):
                 assert torch.equal(e[j], ref), (batch, lo, hi, blur, j, "bgr")
                 assert torch.equal(eg[j], ref), (batch, lo, hi, blur, j, "gray")
     engine.check()
+
+
+def test_canny_three_channel_input(engine, golden_inputs):
+    """cv2.Canny accepts a 3-channel image: Sobel per channel, the strongest channel per pixel.
+    Engine and cv_shim against the live cv2 wheel and the oracle, fixtures and ragged random images, then the edge
+    lists it leaves feed HoughLines like the fused chain's."""
+    import cv2
+    from graphics_project_b200 import cv_shim
+    imgs = [golden_inputs[k] for k in ("demo_scarce", "sc_minecraft_cave", "sc_cube")]
+    rng = np.random.default_rng(7)
+    imgs += [rng.integers(0, 256, (int(h), int(w), 3), dtype=np.uint8) for h, w in ((1, 1), (2, 7), (33, 65), (97, 130))]
+    for img in imgs:
+        for lo, hi in ((5, 150), (30, 50), (120, 40)):
+            want = cv2.Canny(img, lo, hi)
+            assert np.array_equal(R.canny(img, lo, hi), want)
+            got = engine.canny_c3(torch.from_numpy(img).cuda()[None], lo, hi)[0].cpu().numpy()
+            assert np.array_equal(got, want), (img.shape, lo, hi, int((got != want).sum()))
+    img = imgs[0]
+    assert np.array_equal(cv_shim.Canny(img, 5, 150), cv2.Canny(img, 5, 150))
+    e = engine.canny_c3(torch.from_numpy(img).cuda()[None], 5, 150)
+    lines, _, counts, _ = engine.hough_lines(None, 1, np.pi / 180, 50)
+    ref = cv2.HoughLines(e[0].cpu().numpy(), 1, np.pi / 180, 50)
+    assert int(counts[0]) == len(ref) and np.array_equal(lines[0, :len(ref)].cpu().numpy(), ref[:, 0])
+    engine.check()
