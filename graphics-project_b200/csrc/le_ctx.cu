@@ -31,7 +31,12 @@ int le_ensure(le_ctx *ctx, le_buf *b, size_t bytes)
         b->p = nullptr;
         return le_fail(ctx, LE_ERR_NOMEM, "cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
     }
+    // The clear runs on the legacy default stream, which does not order against the non-blocking streams the
+    // callers launch on: without this wait a kernel of the same call could start while the new buffer is still
+    // being zeroed under it (seen as an illegal address in the first call of a freshly created context when
+    // several contexts were warming up at once).  Growth is rare, so the wait costs nothing.
     cudaMemset(b->p, 0, want);
+    cudaDeviceSynchronize();
     b->bytes = want;
     ctx->ws_bytes += want;
     return LE_OK;
