@@ -155,3 +155,39 @@ def test_device_is_restored_after_calls(engine):
         assert torch.cuda.current_device() == 1 and e.device.index == 0
     finally:
         torch.cuda.set_device(0)
+
+
+def test_fresh_contexts_on_concurrent_streams(engine):
+    """The first call of a freshly created context allocates and clears its scratch; three contexts doing that at
+    once on their own (non-blocking) streams must not see a buffer being cleared under a running kernel
+    (le_ensure used to clear on the legacy default stream without waiting: intermittent illegal address in the
+    multi-stream host pipelines)."""
+    u = np.stack([gp.synth.make_frame(s, 540, 960, "voxel") for s in range(6)])
+    t = torch.from_numpy(np.concatenate([u] * 4)).cuda()  # 24 frames
+    gray = engine.bgr2gray(t)
+    want_s, _, _, want_c = engine.lsd(gray, max_segs=1024)
+    edges = engine.front_canny(t, 5, 150)
+    want_p, want_pc = engine.hough_lines_p(edges, 1, np.pi / 180, 30, 50, 10, max_segs=512)
+    torch.cuda.synchronize()
+    for rep in range(3):
+        engs = [gp.Engine(0) for _ in range(3)]
+        streams = [torch.cuda.Stream() for _ in range(3)]
+        outs = []
+        for e, s in zip(engs, streams):
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                g = e.bgr2gray(t)
+                segs, _, _, c = e.lsd(g, max_segs=1024)
+                ed = e.front_canny(t, 5, 150)
+                p, pc = e.hough_lines_p(ed, 1, np.pi / 180, 30, 50, 10, max_segs=512)
+                outs.append((segs, c, p, pc))
+        torch.cuda.synchronize()
+        for e in engs:
+            e.check()
+        for segs, c, p, pc in outs:
+            assert torch.equal(c, want_c) and torch.equal(pc, want_pc)
+            for i in range(24):
+                assert torch.equal(segs[i, :int(c[i])], want_s[i, :int(c[i])])
+                assert torch.equal(p[i, :int(pc[i])], want_p[i, :int(pc[i])])
+        for e in engs:
+            e.close()
