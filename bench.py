@@ -526,9 +526,11 @@ def run_engine(args, wl, rank, world, local_rank):
     eng = run.eng
     state = {"pending": None, "gathered": None}
 
+    no_gather = os.environ.get("LE_BENCH_NO_GATHER") == "1"  # experiments only (scripts/nccl_channels.sh)
+
     def step():
         run.step()
-        if world > 1:  # gather the per-frame results of the whole job, one step behind
+        if world > 1 and not no_gather:  # gather the per-frame results of the whole job, one step behind
             if state["pending"] is not None:
                 state["gathered"] = state["pending"].wait()
             c, p = run.gather_args()
@@ -570,10 +572,15 @@ def run_engine(args, wl, rank, world, local_rank):
     launches = eng.launches - launches0
     clocks = sampler.finish()
     eng.check()
+    ms_ranks = [ms]
     if world > 1:
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+        # every rank's own time (ranks draw different frames, so they differ by a few per cent); the step time of
+        # the job is the slowest rank's
+        tl = torch.zeros((world,), dtype=torch.float64, device=dev)
+        tl[rank] = ms
+        dist.all_reduce(tl)
+        ms_ranks = [float(v) for v in tl.tolist()]
+        ms = max(ms_ranks)
         lt = torch.tensor([launches], dtype=torch.int64, device=dev)
         dist.all_reduce(lt)
         launches = int(lt.item())
@@ -677,6 +684,7 @@ def run_engine(args, wl, rank, world, local_rank):
                 "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": cfg,
                 "results_per_frame_mean": results_mean,
+                "ms_per_step_ranks": [round(v / args.steps, 4) for v in ms_ranks],
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "parity_sample": parity,
                 "gpu_launches": launches, "clocks": clocks}
         print(json.dumps(line), flush=True)
