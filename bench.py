@@ -639,8 +639,10 @@ def run_engine(args, wl, rank, world, local_rank):
             pipe.run(host_frames, *outs)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
-        # copy-only ceiling: the same pinned batch through the same chunks and streams, no kernels
-        ceil_steps = 2
+        # copy-only ceiling: the same pinned batch through the same chunks and streams, no kernels; the ranks start
+        # together (barrier) and copy as many steps as the e2e leg ran, so every rank sees the others' traffic
+        barrier()
+        ceil_steps = e2e_steps
         t0 = time.perf_counter()
         for _ in range(ceil_steps):
             for ci, c0 in enumerate(range(0, B, pipe.chunk)):

@@ -646,6 +646,7 @@ __global__ void k_zero_peaks(int *counters, int n)
         counters[i * LE_C_STRIDE + LE_C_PEAKS] = 0;
         counters[i * LE_C_STRIDE + LE_C_AUX0] = 0;  // vote CTAs of the frame that have finished
         counters[i * LE_C_STRIDE + LE_C_AUX1] = 0;  // peak candidates on stripe-boundary rows
+        counters[i * LE_C_STRIDE + LE_C_OVERFLOW] &= ~4;  // "peak list full" belongs to one call
     }
 }
 

@@ -588,17 +588,23 @@ static __device__ int lsd_grow(volatile u32 *an, const float2 *__restrict__ cs, 
             csn = __ldg(cs + (size_t)yy * W + xx);  // read-only plane; garbage where the angle is undefined (never used)
         }
         bool avail = v != LSD_NOTDEF && !(v & LSD_USED);
+        const double a_l = (double)__uint_as_float(v) * D2R;  // this lane's neighbour's level-line angle
         for (int gg = 0; gg < m; gg++) {
-            // visit only the neighbours that are defined and free, in (yy, xx) scan order
-            u32 candm = (__ballot_sync(~0u, avail) >> (9 * gg)) & 0x1ffu;
+            // The neighbours that are defined and free are visited in (yy, xx) scan order.  Every lane tests ITS
+            // neighbour against the current region angle at once; the first aligned one in scan order is accepted
+            // (which moves the angle), the ones before it were rejected at that angle and stay rejected for this
+            // entry, the ones behind it are tested again at the new angle -- the sequential scan, with rejected
+            // candidates costing nothing.
+            u32 remaining = (__ballot_sync(~0u, avail) >> (9 * gg)) & 0x1ffu;
             const int cpx = __shfl_sync(~0u, px, 9 * gg), cpy = __shfl_sync(~0u, py, 9 * gg);
-            while (candm) {
-                const int k = __ffs(candm) - 1;
-                candm &= candm - 1;
+            while (remaining) {
+                const bool al = aligned_to(reg_angle, a_l, tol) && avail;
+                const u32 mm = (__ballot_sync(~0u, al) >> (9 * gg)) & remaining;
+                if (!mm) break;
+                const int k = __ffs(mm) - 1;
+                remaining &= ~((2u << k) - 1u);
                 const int src = 9 * gg + k;
                 u32 vk = __shfl_sync(~0u, v, src);
-                double a = (double)__uint_as_float(vk) * D2R;
-                if (!aligned_to(reg_angle, a, tol)) continue;
                 int ax = cpx + (k % 3) - 1, ay = cpy + (k / 3) - 1;
                 if (lane == 0) {
                     u32 e = ((u32)ay << 16) | (u32)ax;
@@ -1069,9 +1075,11 @@ static __device__ __forceinline__ u32 ld_cg(const u32 *p)
     return v;
 }
 
+#ifndef SG_HASH
 #define SG_HASH 1024                 // per-warp exact set of the region's pixels (open addressing, shared memory)
 #define SG_HASH_CAP 768              // a larger region waits to be the first of a round
-static __device__ __forceinline__ u32 sg_hash(u32 e) { return (e * 2654435761u) >> 22; }
+#endif
+static __device__ __forceinline__ u32 sg_hash(u32 e) { return ((e * 2654435761u) >> 16) & (SG_HASH - 1); }
 
 static __device__ int lsd_grow_spec(volatile u32 *an, volatile u32 *own, const float2 *__restrict__ cs, u32 *reg,
                                     int reg_cap, u32 *ring, u32 *hset, int W, int H, int sx, int sy, double tol,
@@ -1132,17 +1140,18 @@ static __device__ int lsd_grow_spec(volatile u32 *an, volatile u32 *own, const f
             }
         }
         avail = avail && !taken && !mine;
+        const double a_l = (double)__uint_as_float(v) * D2R;  // this lane's neighbour's level-line angle
         for (int gg = 0; gg < m && !full; gg++) {
-            u32 candm = (__ballot_sync(~0u, avail) >> (9 * gg)) & 0x1ffu;
+            u32 remaining = (__ballot_sync(~0u, avail) >> (9 * gg)) & 0x1ffu;  // (see lsd_grow)
             const int cpx = __shfl_sync(~0u, px, 9 * gg), cpy = __shfl_sync(~0u, py, 9 * gg);
-            while (candm) {
-                const int k = __ffs(candm) - 1;
-                candm &= candm - 1;
-                const int src = 9 * gg + k;
-                u32 vk = __shfl_sync(~0u, v, src);
-                double a = (double)__uint_as_float(vk) * D2R;
-                if (!aligned_to(reg_angle, a, tol)) continue;
+            while (remaining) {
+                const bool al = aligned_to(reg_angle, a_l, tol) && avail;
+                const u32 mm = (__ballot_sync(~0u, al) >> (9 * gg)) & remaining;
+                if (!mm) break;
                 if (n >= reg_cap || n >= SG_HASH_CAP) { full = true; break; }
+                const int k = __ffs(mm) - 1;
+                remaining &= ~((2u << k) - 1u);
+                const int src = 9 * gg + k;
                 int ax = cpx + (k % 3) - 1, ay = cpy + (k / 3) - 1;
                 if (lane == 0) {
                     u32 e = ((u32)ay << 16) | (u32)ax;

@@ -191,3 +191,60 @@ def test_fresh_contexts_on_concurrent_streams(engine):
                 assert torch.equal(p[i, :int(pc[i])], want_p[i, :int(pc[i])])
         for e in engs:
             e.close()
+
+
+def test_houghp_dense_frames_use_the_global_order_path(engine):
+    """Noise frames: far more edge pixels than the shared-memory list of k_ppht_order holds (the shuffle then runs
+    in place in global memory), thousands of triggers, almost no accepted segment -- still cv2's exact result."""
+    rng = np.random.default_rng(11)
+    frames = rng.integers(0, 256, (3, 270, 480), dtype=np.uint8)
+    frames[2, 100:170] = 90  # a flat band: long runs without edge pixels
+    t = torch.from_numpy(frames).cuda()
+    edges = engine.canny(t, 40, 120)
+    assert int((edges[0] != 0).sum()) > 20000
+    segs, counts = engine.hough_lines_p(edges, 1, np.pi / 180, 30, 20, 3, max_segs=8192)
+    engine.check()
+    for i in range(3):
+        e = edges[i].cpu().numpy()
+        assert np.array_equal(e, R.canny(frames[i], 40, 120))
+        sp = R.hough_lines_p(e, 1, np.pi / 180, 30, 20, 3)
+        n = 0 if sp is None else len(sp)
+        assert int(counts[i]) == n
+        if n:
+            assert np.array_equal(segs[i, :n].cpu().numpy(), sp[:, 0])
+
+
+def test_refused_parameters_and_reported_overflow(engine):
+    """What the engine cannot do exactly it refuses (never a silent wrong answer): rho beyond the 16-bit counters,
+    the order-free HoughLinesP mode, ambiguous / malformed tensors; a peak list that overflows is reported by
+    check()."""
+    z = torch.zeros((1, 1080, 1920), dtype=torch.uint8, device="cuda")
+    with pytest.raises(gp.EngineError) as ei:
+        engine.hough_lines(z, 40.0, np.pi / 180, 50)
+    assert ei.value.code == -5
+    with pytest.raises(gp.EngineError) as ei:
+        engine.hough_lines_p(z, 40.0, np.pi / 180, 30, 50, 10)
+    assert ei.value.code == -5
+    with pytest.raises(gp.EngineError) as ei:
+        engine.hough_lines_p(z, 1, np.pi / 180, 30, 50, 10, exact_order=False)
+    assert ei.value.code == -5 and "order" in str(ei.value)
+    with pytest.raises(ValueError):
+        engine.front_canny(torch.zeros((64, 64, 3), dtype=torch.uint8, device="cuda"), 5, 10)
+    with pytest.raises(ValueError):
+        engine.front_canny(z, 5, 10, out=torch.zeros((1, 1080, 1919), dtype=torch.uint8, device="cuda"))
+    with pytest.raises(TypeError):
+        engine.front_canny(z, 5, 10, out=torch.zeros((1, 1080, 1920), dtype=torch.int32, device="cuda"))
+    with pytest.raises(ValueError):
+        engine.hough_lines(z, 1, np.pi / 180, 50, out=(torch.zeros((1, 64, 2), device="cuda"), None,
+                                                      torch.zeros((2,), dtype=torch.int32, device="cuda"), None))
+    # more local maxima than the peak list holds: counts still says how many, check() says the lines are unreliable
+    rng = np.random.default_rng(5)
+    noise = torch.from_numpy((rng.random((1, 1080, 1920)) < 0.3).astype(np.uint8) * 255).cuda()
+    lines, _, counts, _ = engine.hough_lines(noise, 1, np.pi / 180, 2, max_lines=256)
+    assert int(counts[0]) > 65536
+    with pytest.raises(gp.EngineError) as ei:
+        engine.check()
+    assert ei.value.code == -4
+    # the flag is per call: the next call on the same context is clean again
+    engine.hough_lines(z, 1, np.pi / 180, 50)
+    engine.check()
