@@ -147,7 +147,7 @@ __global__ void __launch_bounds__(PR_THREADS)
 k_ppht_rounds(u8 *__restrict__ mask, const u32 *__restrict__ nz_g, u32 *__restrict__ accum,
               const float *__restrict__ trig, const int *__restrict__ counters, int32_t *__restrict__ segs,
               int32_t *__restrict__ counts, int max_segs, int h, int w, int numangle, int stride, int threshold,
-              int line_length, int line_gap, int round_cap)
+              int line_length, int line_gap, int round_cap, int flags)
 {
     constexpr int PR_B = 32 * NH;
     __shared__ PRShared S;
@@ -175,6 +175,9 @@ k_ppht_rounds(u8 *__restrict__ mask, const u32 *__restrict__ nz_g, u32 *__restri
     // behind a trigger are issued and taken back), doubled after a round that did not.  Cube frames trigger in
     // ~40 % of the rounds and stay at the cap; cave-style frames trigger in ~90 % and settle at 8
     int cap_now = round_cap, streak = 0;
+    // (Fetching the NEXT round's mask bytes while the votes are in flight -- valid when the round does not trigger --
+    // was measured and dropped: the extra scattered loads cost more than the round trip they hide, 256 x 1080p
+    // 5.5 -> 6.9 ms, profiles/r2_ppht_variants.txt.)
 #ifdef LE_PPHT_PROFILE  // phase cycle counters of frame 0 (variant build, scripts/ppht_profile.sh)
     long long dbg[8] = {0, 0, 0, 0, 0, 0, 0, 0}, cnt_[6] = {0, 0, 0, 0, 0, 0}, t_a = clock64();
 #define PR_TICK(i) do { if (tid == 0) { long long t_ = clock64(); dbg[i] += t_ - t_a; t_a = t_; } } while (0)
@@ -277,7 +280,7 @@ k_ppht_rounds(u8 *__restrict__ mask, const u32 *__restrict__ nz_g, u32 *__restri
             streak = 0;
             continue;
         }
-        if (++streak >= 2) cap_now = max(min(8, round_cap), cap_now >> 1);
+        if ((flags & 1) && ++streak >= 2) cap_now = max(min(8, round_cap), cap_now >> 1);
         // ---- trigger at candidate ks: arg-max over the angles (highest value, then lowest angle)
         {
             const u32 key = (my_first == ks) ? (((u32)(my_val + 0x8000) << 8) | (u32)(255 - tid)) : 0u;
@@ -489,11 +492,13 @@ int le_ppht_rounds_launch(le_ctx *ctx, int n, int h, int w, int numangle, int st
     const int knob = LE_KNOB_INT("LE_PPHT_B", 0);  // development knob
     const int round_cap = std::max(1, std::min(128, knob ? knob : round_dflt));
     const int nh = (round_cap + 31) / 32;
+    // development knob: LE_PPHT_NOADAPT=1 keeps the round size fixed (128 cave frames: 22.7 -> 34.5 ms)
+    const int flags = LE_KNOB_SET("LE_PPHT_NOADAPT") ? 0 : 1;
 #define LE_ROUNDS(NH)                                                                                             \
     k_ppht_rounds<NH><<<n, PR_THREADS, 0, st>>>((u8 *)ctx->ppht_mask.p, (const u32 *)ctx->ppht_nz.p,              \
                                                 (u32 *)ctx->ppht_accum.p, (const float *)ctx->trig.p,             \
                                                 (const int *)ctx->counters.p, segs, counts, max_segs, h, w,       \
-                                                numangle, stride, threshold, min_len, max_gap, round_cap)
+                                                numangle, stride, threshold, min_len, max_gap, round_cap, flags)
     if (nh == 1) LE_ROUNDS(1);
     else if (nh == 2) LE_ROUNDS(2);
     else LE_ROUNDS(4);

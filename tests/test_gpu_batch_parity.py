@@ -239,7 +239,7 @@ def test_refused_parameters_and_reported_overflow(engine):
                                                       torch.zeros((2,), dtype=torch.int32, device="cuda"), None))
     # more local maxima than the peak list holds: counts still says how many, check() says the lines are unreliable
     rng = np.random.default_rng(5)
-    noise = torch.from_numpy((rng.random((1, 1080, 1920)) < 0.3).astype(np.uint8) * 255).cuda()
+    noise = torch.from_numpy((rng.random((1, 2160, 3840)) < 0.3).astype(np.uint8) * 255).cuda()
     lines, _, counts, _ = engine.hough_lines(noise, 1, np.pi / 180, 2, max_lines=256)
     assert int(counts[0]) > 65536
     with pytest.raises(gp.EngineError) as ei:
