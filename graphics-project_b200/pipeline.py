@@ -54,6 +54,18 @@ def bind_to_gpu_numa_node(device_index):
     return info
 
 
+class Pending:
+    """A batch enqueued with ``run(..., wait=False)``."""
+
+    def __init__(self, events, outs):
+        self.events, self.outs = events, outs
+
+    def wait(self):
+        for e in self.events:
+            e.synchronize()
+        return self.outs
+
+
 class _ChunkedHost:
     """``streams`` CUDA streams, each with its own engine context and device buffers, take the chunks in turn;
     subclasses say what a chunk needs and does.  Two streams hide the copy behind the kernels of a bandwidth-bound
@@ -78,9 +90,13 @@ class _ChunkedHost:
     def _chunk(self, eng, b, k):  # enqueue the chain on the current stream; -> list of device result tensors [k, ...]
         raise NotImplementedError
 
-    def run(self, frames, *outs):
-        """frames [N,H,W,3] u8 and every tensor of ``outs``: pinned host tensors.  Blocks until every result is in
-        host memory.  ``outs`` are filled in the order the chain's results are documented."""
+    def run(self, frames, *outs, wait=True):
+        """frames [N,H,W,3] u8 and every tensor of ``outs``: pinned host tensors, filled in the order the chain's
+        results are documented.  With ``wait`` (default) the call blocks until every result is in host memory.
+        ``wait=False`` only enqueues the batch and returns a ``Pending`` whose ``wait()`` blocks for THIS batch: a
+        caller that alternates two sets of output buffers can enqueue batch i + 1 before it waits for batch i, so
+        the kernels of the last chunks of a batch run beside the first copies of the next one (device buffers are
+        reused in stream order, which makes that safe)."""
         n = frames.shape[0]
         self.h2d_bytes = self.d2h_bytes = 0
         for ci, c0 in enumerate(range(0, n, self.chunk)):
@@ -96,9 +112,13 @@ class _ChunkedHost:
                     o[c0:c1].copy_(r, non_blocking=True)
                     self.d2h_bytes += r.numel() * r.element_size()
             self.h2d_bytes += frames[c0:c1].numel()
+        events = []
         for s in self.streams:
-            s.synchronize()
-        return outs
+            e = torch.cuda.Event()
+            e.record(s)
+            events.append(e)
+        pending = Pending(events, outs)
+        return pending.wait() if wait else pending
 
     @property
     def launches(self):
