@@ -198,24 +198,28 @@ def hbm_peak():
 
 
 class ClockSampler(threading.Thread):
-    """Samples nvidia-smi SM clocks and throttle reasons while the timed region runs."""
+    """Samples nvidia-smi SM clocks and throttle reasons while the timed region runs.  ONE sampler per job (rank 0)
+    queries every GPU of the job in one call every 200 ms: a sampler per rank put N times as many nvidia-smi
+    processes on the driver, which showed up as a step time that grew with N."""
 
-    def __init__(self, index):
+    def __init__(self, indices):
         super().__init__(daemon=True)
-        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+        self.ids, self.rows, self._stop_evt = ",".join(str(i) for i in indices), [], threading.Event()
 
     def run(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         while not self._stop_evt.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                out = subprocess.run(["nvidia-smi", f"--id={self.ids}", f"--query-gpu={q}",
                                       "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
-                if out.returncode == 0 and out.stdout.strip():
-                    self.rows.append([c.strip() for c in out.stdout.strip().split(",")])
+                if out.returncode == 0:
+                    for ln in out.stdout.strip().splitlines():
+                        if ln.strip():
+                            self.rows.append([c.strip() for c in ln.split(",")])
             except Exception:
                 pass
-            self._stop_evt.wait(0.1)
+            self._stop_evt.wait(0.2)
 
     def finish(self):
         self._stop_evt.set()
@@ -225,8 +229,9 @@ class ClockSampler(threading.Thread):
         sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows)]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]),
-                "reasons": reasons, "samples": len(self.rows)}
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_min_mhz": sm[0] if sm else None,
+                "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons, "samples": len(self.rows),
+                "gpus_sampled": self.ids}
 
 
 def load_synth():
@@ -552,8 +557,10 @@ def run_engine(args, wl, rank, world, local_rank):
     drain()
     barrier()
     eng.check()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    # one process samples every GPU of the job (LE_BENCH_NO_SAMPLER=1: experiments only)
+    sampler = ClockSampler(range(world)) if rank == 0 and os.environ.get("LE_BENCH_NO_SAMPLER") != "1" else None
+    if sampler:
+        sampler.start()
     t_load = time.perf_counter()
     while time.perf_counter() - t_load < 1.0:  # keep the GPU under load while the clock sampler collects
         step()
@@ -570,7 +577,7 @@ def run_engine(args, wl, rank, world, local_rank):
     barrier()
     ms = ev0.elapsed_time(ev1)
     launches = eng.launches - launches0
-    clocks = sampler.finish()
+    clocks = sampler.finish() if sampler else None
     eng.check()
     ms_ranks = [ms]
     if world > 1:
