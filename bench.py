@@ -522,7 +522,12 @@ def run_engine(args, wl, rank, world, local_rank):
     B = args.batch or wl.batch
 
     # ---- synthetic input: frames are generated on the host once and uploaded before timing
-    _, uniq = make_frames(synth, wl, min(wl.unique, B), rank if args.seed_rank < 0 else args.seed_rank)
+    # The job's batch is the workload's `unique` distinct frames tiled cyclically over all B x N slots (generation
+    # cost only), so every GPU holds the same frames and the per-GPU work is exactly fixed as N grows (weak scaling).
+    # --rank-seeds gives every rank its own frames instead (seed + 1000 * rank): step times then differ by up to
+    # 5 % with the content and the job runs at the slowest rank's pace (profiles/r2_seed_rank_step_times.txt).
+    seed_rank = args.seed_rank if args.seed_rank >= 0 else (rank if args.rank_seeds else 0)
+    _, uniq = make_frames(synth, wl, min(wl.unique, B), seed_rank)
     host_frames = torch.empty((B, wl.h, wl.w, 3), dtype=torch.uint8, pin_memory=True)
     for i in range(B):
         host_frames[i] = torch.from_numpy(uniq[i % len(uniq)])
@@ -700,6 +705,8 @@ def run_engine(args, wl, rank, world, local_rank):
     if rank == 0:
         cfg = wl.config()
         cfg["batch_per_gpu"] = B
+        if args.rank_seeds or args.seed_rank >= 0:
+            cfg["frames"] = "per-rank seeds" if args.rank_seeds else f"seed rank {args.seed_rank}"
         line = {"metric": wl.metric, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": cfg,
@@ -726,7 +733,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--no-numa", action="store_true", help="do not bind the process to the GPU's NUMA node")
-    ap.add_argument("--seed-rank", type=int, default=-1, help="generate the frames rank R of a multi-GPU run would get")
+    ap.add_argument("--rank-seeds", action="store_true", help="every rank draws its own frames (seed + 1000 * rank)")
+    ap.add_argument("--seed-rank", type=int, default=-1, help="generate the frames rank R of a --rank-seeds run gets")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
