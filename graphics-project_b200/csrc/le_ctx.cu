@@ -42,7 +42,7 @@ int le_ensure(le_ctx *ctx, le_buf *b, size_t bytes)
     return LE_OK;
 }
 
-extern "C" const char *le_version(void) { return "lineengine 0.1 sm_100a"; }
+extern "C" const char *le_version(void) { return "lineengine 0.2 sm_100a"; }
 
 extern "C" int le_create(le_ctx **out, int device, int max_h, int max_w, int max_batch)
 {
