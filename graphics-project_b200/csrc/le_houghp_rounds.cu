@@ -175,6 +175,8 @@ k_ppht_rounds(u8 *__restrict__ mask, const u32 *__restrict__ nz_g, u32 *__restri
     // behind a trigger are issued and taken back), doubled after a round that did not.  Cube frames trigger in
     // ~40 % of the rounds and stay at the cap; cave-style frames trigger in ~90 % and settle at 8
     int cap_now = round_cap, streak = 0;
+    // (A second group of 192 threads taking one direction of the erase / un-vote pass was also measured: no gain at
+    // 128 x 4K, 256 x 1080p 5.5 -> 5.9 ms, 1024 x 1080p 26.9 -> 25.2 ms -- that pass is bound by the request rate too.)
     // (Fetching the NEXT round's mask bytes while the votes are in flight -- valid when the round does not trigger --
     // was measured and dropped: the extra scattered loads cost more than the round trip they hide, 256 x 1080p
     // 5.5 -> 6.9 ms, profiles/r2_ppht_variants.txt.)
