@@ -515,6 +515,7 @@ def run_engine(args, wl, rank, world, local_rank):
     assert torch.cuda.is_available(), "bench.py needs a GPU (the engine has no CPU fallback)"
     synth = load_synth()
     torch.cuda.set_device(local_rank)
+    affinity0 = os.sched_getaffinity(0)  # the CPU leg below gets every core back
     numa = gp.pipeline.bind_to_gpu_numa_node(local_rank) if not args.no_numa else {"bound": False, "skipped": True}
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -692,6 +693,7 @@ def run_engine(args, wl, rank, world, local_rank):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         import cv2 as cv
+        os.sched_setaffinity(0, affinity0)
         sample = max(1, min(128, wl.ref_step_frames_per_core * (os.cpu_count() or 1) * 2))
         fl = [uniq[i % len(uniq)] for i in range(sample)]
         fps_cpu, cores, dt, done, kind = time_cpu_reference(wl, fl)
