@@ -17,6 +17,16 @@
  *   - Scratch memory is owned by the opaque context and grows on demand (first call of a
  *     given size allocates; steady state does not).  A context is bound to one device and is
  *     not thread-safe; use one context per (process, device, stream).
+ *     Several contexts may live in one process, on the same or on different devices; every entry
+ *     point runs on its context's device and restores the caller's current device before it
+ *     returns.  A call that has to grow scratch waits for the device once (allocation + clear).
+ *   - Parameter combinations the kernels cannot handle exactly (16-bit vote counters, an order-free
+ *     HoughLinesP) return LE_ERR_UNSUPPORTED; an internal list that overflowed (edge queue, Hough
+ *     peak list) is reported by le_check as LE_ERR_OVERFLOW.  Nothing is silently approximated.
+ *   - The reference-level geometry entries (le_pair_intersections, le_segments_to_polar,
+ *     le_combine_parallel_lines, le_face_quads, le_vp_*) compute in float64 where the reference's
+ *     numpy stays in float32 for float32 inputs, and le_vp_fit_batch is a deterministic search where
+ *     the reference draws random candidates: INTEGRATION.md lists these differences.
  *   - Variable-length results use caller-provided padded buffers [n][max_k][...] plus
  *     counts[n] (int32).  counts[i] holds the TRUE count even if it exceeds max_k (only
  *     max_k entries are written), so the caller can detect truncation and retry.
